@@ -1,0 +1,377 @@
+/* Host-side FLAC / WAV reader for bl_audio_decode.
+ *
+ * The reference demuxes/decodes with FFmpeg (reference src/decode.c:27-213); this
+ * container has no FFmpeg, so the drop-in carries its own small decoders for the
+ * container formats its fixtures and benchmarks use: native FLAC (all subframe
+ * types, 8..24 bit, 1..2 channels used here, up to 8 decoded) and RIFF/WAVE PCM
+ * (s16 / s24 / s32 / f32). Output: interleaved int32 samples at the file's own
+ * bit depth + STREAMINFO + Vorbis comments. Conversion to the analysers' input
+ * format (int16, 22 050 Hz, stereo) happens in decode.c.
+ *
+ * Written from the FLAC format specification (RFC 9639); not derived from
+ * libFLAC or FFmpeg source.
+ */
+#include "flac_reader.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+
+/* ------------------------------------------------------------------ */
+/* bit reader                                                          */
+/* ------------------------------------------------------------------ */
+typedef struct {
+    const uint8_t *p;
+    size_t n;
+    size_t pos;   /* next byte to load */
+    uint64_t acc; /* bit accumulator, MSB-first, valid bits in the low `cnt` */
+    int cnt;
+    int err;
+} bitrd;
+
+static void br_init(bitrd *b, const uint8_t *p, size_t n, size_t pos) {
+    b->p = p; b->n = n; b->pos = pos; b->acc = 0; b->cnt = 0; b->err = 0;
+}
+
+static inline void br_fill(bitrd *b, int need) {
+    while (b->cnt < need) {
+        uint64_t byte = 0;
+        if (b->pos < b->n) byte = b->p[b->pos];
+        else b->err = 1;
+        b->pos++;
+        b->acc = (b->acc << 8) | byte;
+        b->cnt += 8;
+    }
+}
+
+static inline uint32_t br_u(bitrd *b, int nbits) { /* nbits <= 32 */
+    if (nbits == 0) return 0;
+    br_fill(b, nbits);
+    b->cnt -= nbits;
+    return (uint32_t)((b->acc >> b->cnt) & ((nbits == 32) ? 0xFFFFFFFFu : ((1u << nbits) - 1u)));
+}
+
+static inline int32_t br_s(bitrd *b, int nbits) {
+    uint32_t v = br_u(b, nbits);
+    if (nbits == 0) return 0;
+    if (nbits < 32 && (v >> (nbits - 1))) v |= ~((1u << nbits) - 1u);
+    return (int32_t)v;
+}
+
+static inline uint32_t br_unary(bitrd *b) { /* count zeros before the next 1 bit */
+    uint32_t z = 0;
+    for (;;) {
+        if (b->cnt == 0) {
+            br_fill(b, 8);
+            if (b->err) return z;
+        }
+        uint64_t window = b->acc & ((b->cnt == 64) ? ~0ull : ((1ull << b->cnt) - 1ull));
+        if (window == 0) {
+            z += (uint32_t)b->cnt;
+            b->cnt = 0;
+            continue;
+        }
+        int top = 63 - __builtin_clzll(window); /* position of the first 1 */
+        z += (uint32_t)(b->cnt - 1 - top);
+        b->cnt = top;                          /* consume zeros and the 1 */
+        return z;
+    }
+}
+
+static inline void br_align(bitrd *b) { b->cnt -= (b->cnt & 7); }
+static inline size_t br_bytepos(const bitrd *b) { return b->pos - (size_t)(b->cnt >> 3); }
+
+/* ------------------------------------------------------------------ */
+/* FLAC                                                                */
+/* ------------------------------------------------------------------ */
+static int read_residual(bitrd *b, int32_t *out, int blocksize, int pred_order) {
+    int method = (int)br_u(b, 2);
+    if (method > 1) return -1;
+    int pbits = method ? 5 : 4;
+    uint32_t escape = method ? 31u : 15u;
+    int porder = (int)br_u(b, 4);
+    int nparts = 1 << porder;
+    if ((blocksize >> porder) << porder != blocksize && porder > 0) return -1;
+    int idx = pred_order;
+    for (int part = 0; part < nparts; ++part) {
+        int count = (blocksize >> porder) - (part == 0 ? pred_order : 0);
+        if (count < 0) return -1;
+        uint32_t param = br_u(b, pbits);
+        if (param == escape) {
+            int raw = (int)br_u(b, 5);
+            for (int i = 0; i < count; ++i) out[idx++] = br_s(b, raw);
+        } else {
+            for (int i = 0; i < count; ++i) {
+                uint32_t q = br_unary(b);
+                uint32_t r = br_u(b, (int)param);
+                uint32_t u = (q << param) | r;
+                out[idx++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+            }
+        }
+        if (b->err) return -1;
+    }
+    return 0;
+}
+
+static int read_subframe(bitrd *b, int32_t *out, int blocksize, int bps) {
+    if (br_u(b, 1)) return -1; /* padding */
+    int type = (int)br_u(b, 6);
+    int wasted = 0;
+    if (br_u(b, 1)) wasted = (int)br_unary(b) + 1;
+    bps -= wasted;
+    if (bps <= 0 || bps > 33) return -1;
+    if (type == 0) { /* constant */
+        int32_t v = (bps > 32) ? (int32_t)(((int64_t)br_s(b, 1) << 32) | br_u(b, 32)) : br_s(b, bps);
+        for (int i = 0; i < blocksize; ++i) out[i] = v;
+    } else if (type == 1) { /* verbatim */
+        for (int i = 0; i < blocksize; ++i) out[i] = br_s(b, bps > 32 ? 32 : bps);
+    } else if (type >= 8 && type <= 12) { /* fixed predictor */
+        int order = type - 8;
+        if (order > blocksize) return -1;
+        for (int i = 0; i < order; ++i) out[i] = br_s(b, bps);
+        if (read_residual(b, out, blocksize, order)) return -1;
+        for (int i = order; i < blocksize; ++i) {
+            int64_t p = 0;
+            switch (order) {
+                case 1: p = out[i - 1]; break;
+                case 2: p = 2 * (int64_t)out[i - 1] - out[i - 2]; break;
+                case 3: p = 3 * (int64_t)out[i - 1] - 3 * (int64_t)out[i - 2] + out[i - 3]; break;
+                case 4: p = 4 * (int64_t)out[i - 1] - 6 * (int64_t)out[i - 2] + 4 * (int64_t)out[i - 3] - out[i - 4]; break;
+                default: break;
+            }
+            out[i] = (int32_t)(p + out[i]);
+        }
+    } else if (type >= 32) { /* LPC */
+        int order = type - 31;
+        if (order > blocksize) return -1;
+        int32_t coef[32];
+        for (int i = 0; i < order; ++i) out[i] = br_s(b, bps);
+        int prec = (int)br_u(b, 4) + 1;
+        if (prec == 16) return -1;
+        int shift = br_s(b, 5);
+        if (shift < 0) return -1;
+        for (int i = 0; i < order; ++i) coef[i] = br_s(b, prec);
+        if (read_residual(b, out, blocksize, order)) return -1;
+        for (int i = order; i < blocksize; ++i) {
+            int64_t acc = 0;
+            for (int j = 0; j < order; ++j) acc += (int64_t)coef[j] * out[i - 1 - j];
+            out[i] = (int32_t)((acc >> shift) + out[i]);
+        }
+    } else {
+        return -1;
+    }
+    if (wasted)
+        for (int i = 0; i < blocksize; ++i) out[i] = (int32_t)((uint32_t)out[i] << wasted);
+    return b->err ? -1 : 0;
+}
+
+static void add_tag(blx_pcm_file *f, const char *kv, size_t len) {
+    const char *eq = memchr(kv, '=', len);
+    if (!eq) return;
+    size_t klen = (size_t)(eq - kv), vlen = len - klen - 1;
+    static const char *keys[5] = {"TRACKNUMBER", "TITLE", "ARTIST", "ALBUM", "GENRE"};
+    char **dst[5] = {&f->tracknumber, &f->title, &f->artist, &f->album, &f->genre};
+    for (int i = 0; i < 5; ++i) {
+        if (strlen(keys[i]) == klen && strncasecmp(kv, keys[i], klen) == 0 && !*dst[i]) {
+            *dst[i] = (char *)malloc(vlen + 1);
+            memcpy(*dst[i], eq + 1, vlen);
+            (*dst[i])[vlen] = '\0';
+        }
+    }
+}
+
+static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
+    size_t pos = 4;
+    int have_info = 0, last = 0;
+    uint64_t total = 0;
+    while (!last) {
+        if (pos + 4 > n) return -1;
+        last = d[pos] >> 7;
+        int type = d[pos] & 0x7F;
+        size_t len = ((size_t)d[pos + 1] << 16) | ((size_t)d[pos + 2] << 8) | d[pos + 3];
+        pos += 4;
+        if (pos + len > n) return -1;
+        if (type == 0 && len >= 34) {
+            const uint8_t *s = d + pos;
+            f->sample_rate = (int)(((uint32_t)s[10] << 12) | ((uint32_t)s[11] << 4) | (s[12] >> 4));
+            f->channels = ((s[12] >> 1) & 7) + 1;
+            f->bits_per_sample = (((s[12] & 1) << 4) | (s[13] >> 4)) + 1;
+            total = ((uint64_t)(s[13] & 0xF) << 32) | ((uint64_t)s[14] << 24) | ((uint64_t)s[15] << 16) |
+                    ((uint64_t)s[16] << 8) | s[17];
+            memcpy(f->md5, s + 18, 16);
+            have_info = 1;
+        } else if (type == 4 && len >= 8) { /* VORBIS_COMMENT, little-endian lengths */
+            const uint8_t *s = d + pos;
+            size_t o = 0;
+            uint32_t vlen = s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24);
+            o = 4 + (size_t)vlen;
+            if (o + 4 <= len) {
+                uint32_t cnt = s[o] | (s[o + 1] << 8) | (s[o + 2] << 16) | ((uint32_t)s[o + 3] << 24);
+                o += 4;
+                for (uint32_t i = 0; i < cnt && o + 4 <= len; ++i) {
+                    uint32_t l = s[o] | (s[o + 1] << 8) | (s[o + 2] << 16) | ((uint32_t)s[o + 3] << 24);
+                    o += 4;
+                    if (o + l > len) break;
+                    add_tag(f, (const char *)s + o, l);
+                    o += l;
+                }
+            }
+        }
+        pos += len;
+    }
+    if (!have_info || f->channels < 1 || f->channels > 8) return -1;
+    f->is_float = 0;
+
+    size_t cap = total ? (size_t)total : (size_t)1 << 20;
+    int32_t *pcm = (int32_t *)malloc(cap * (size_t)f->channels * sizeof(int32_t));
+    int32_t *chbuf = (int32_t *)malloc((size_t)65536 * 8 * sizeof(int32_t));
+    if (!pcm || !chbuf) { free(pcm); free(chbuf); return -1; }
+    size_t nframes = 0;
+
+    while (pos + 2 <= n) {
+        if (!(d[pos] == 0xFF && (d[pos + 1] & 0xFE) == 0xF8)) { pos++; continue; }
+        bitrd b;
+        br_init(&b, d, n, pos);
+        br_u(&b, 16);
+        int bs_code = (int)br_u(&b, 4);
+        int sr_code = (int)br_u(&b, 4);
+        int ch_code = (int)br_u(&b, 4);
+        int ss_code = (int)br_u(&b, 3);
+        br_u(&b, 1);
+        /* UTF-8 style coded frame/sample number */
+        uint32_t first = br_u(&b, 8);
+        int extra = 0;
+        if (first & 0x80) { uint32_t m = 0x40; while (first & m) { extra++; m >>= 1; } }
+        for (int i = 0; i < extra; ++i) br_u(&b, 8);
+        int blocksize;
+        if (bs_code == 1) blocksize = 192;
+        else if (bs_code >= 2 && bs_code <= 5) blocksize = 576 << (bs_code - 2);
+        else if (bs_code == 6) blocksize = (int)br_u(&b, 8) + 1;
+        else if (bs_code == 7) blocksize = (int)br_u(&b, 16) + 1;
+        else if (bs_code >= 8) blocksize = 256 << (bs_code - 8);
+        else { pos++; continue; }
+        if (sr_code == 12) br_u(&b, 8);
+        else if (sr_code == 13 || sr_code == 14) br_u(&b, 16);
+        br_u(&b, 8); /* CRC-8 (not verified; STREAMINFO md5 is checked by the tests) */
+        static const int ss_tab[8] = {0, 8, 12, 0, 16, 20, 24, 32};
+        int bps = ss_tab[ss_code] ? ss_tab[ss_code] : f->bits_per_sample;
+        int nch = (ch_code < 8) ? ch_code + 1 : 2;
+        if (ch_code > 10 || nch != f->channels || b.err) { pos++; continue; }
+
+        int ok = 1;
+        for (int c = 0; c < nch && ok; ++c) {
+            int side = (ch_code == 8 && c == 1) || (ch_code == 9 && c == 0) || (ch_code == 10 && c == 1);
+            if (read_subframe(&b, chbuf + (size_t)c * 65536, blocksize, bps + side)) ok = 0;
+        }
+        if (!ok) { pos++; continue; }
+        br_align(&b);
+        br_u(&b, 16); /* CRC-16 */
+        if (b.err) break;
+
+        int32_t *c0 = chbuf, *c1 = chbuf + 65536;
+        if (ch_code == 8) { for (int i = 0; i < blocksize; ++i) c1[i] = c0[i] - c1[i]; }
+        else if (ch_code == 9) { for (int i = 0; i < blocksize; ++i) c0[i] = c0[i] + c1[i]; }
+        else if (ch_code == 10) {
+            for (int i = 0; i < blocksize; ++i) {
+                int32_t side = c1[i];
+                int32_t mid = (int32_t)(((uint32_t)c0[i] << 1) | (uint32_t)(side & 1));
+                c0[i] = (mid + side) >> 1;
+                c1[i] = (mid - side) >> 1;
+            }
+        }
+        if (nframes + (size_t)blocksize > cap) {
+            cap = (nframes + (size_t)blocksize) * 2;
+            int32_t *np = (int32_t *)realloc(pcm, cap * (size_t)nch * sizeof(int32_t));
+            if (!np) { free(pcm); free(chbuf); return -1; }
+            pcm = np;
+        }
+        for (int i = 0; i < blocksize; ++i)
+            for (int c = 0; c < nch; ++c)
+                pcm[(nframes + (size_t)i) * (size_t)nch + (size_t)c] = chbuf[(size_t)c * 65536 + (size_t)i];
+        nframes += (size_t)blocksize;
+        pos = br_bytepos(&b);
+    }
+    free(chbuf);
+    if (total && nframes > total) nframes = (size_t)total;
+    f->samples = pcm;
+    f->n_frames = nframes;
+    return nframes ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------ */
+/* RIFF / WAVE                                                         */
+/* ------------------------------------------------------------------ */
+static uint32_t le32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+static int decode_wav(const uint8_t *d, size_t n, blx_pcm_file *f) {
+    size_t pos = 12;
+    int fmt_tag = 0, have_fmt = 0;
+    while (pos + 8 <= n) {
+        uint32_t len = le32(d + pos + 4);
+        const uint8_t *body = d + pos + 8;
+        if (pos + 8 + len > n) len = (uint32_t)(n - pos - 8);
+        if (!memcmp(d + pos, "fmt ", 4) && len >= 16) {
+            fmt_tag = le16(body);
+            f->channels = le16(body + 2);
+            f->sample_rate = (int)le32(body + 4);
+            f->bits_per_sample = le16(body + 14);
+            if (fmt_tag == 0xFFFE && len >= 26) fmt_tag = le16(body + 24);
+            have_fmt = 1;
+        } else if (!memcmp(d + pos, "data", 4) && have_fmt) {
+            int bytes = f->bits_per_sample / 8;
+            if (bytes < 1 || bytes > 4 || f->channels < 1) return -1;
+            size_t total = len / (size_t)bytes;
+            size_t nframes = total / (size_t)f->channels;
+            f->is_float = (fmt_tag == 3);
+            if (f->is_float && bytes != 4) return -1;
+            int32_t *pcm = (int32_t *)malloc((total ? total : 1) * sizeof(int32_t));
+            if (!pcm) return -1;
+            for (size_t i = 0; i < nframes * (size_t)f->channels; ++i) {
+                const uint8_t *s = body + i * (size_t)bytes;
+                int32_t v;
+                if (bytes == 1) v = (int32_t)s[0] - 128;
+                else if (bytes == 2) v = (int16_t)le16(s);
+                else if (bytes == 3) v = (int32_t)((uint32_t)s[0] << 8 | (uint32_t)s[1] << 16 | (uint32_t)s[2] << 24) >> 8;
+                else v = (int32_t)le32(s); /* s32, or raw f32 bits when is_float */
+                pcm[i] = v;
+            }
+            f->samples = pcm;
+            f->n_frames = nframes;
+            return nframes ? 0 : -1;
+        }
+        pos += 8 + (size_t)len + (len & 1);
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------ */
+int blx_pcm_file_read(const char *filename, blx_pcm_file *f) {
+    memset(f, 0, sizeof(*f));
+    FILE *fp = fopen(filename, "rb");
+    if (!fp) return -1;
+    fseek(fp, 0, SEEK_END);
+    long sz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    if (sz < 16) { fclose(fp); return -1; }
+    uint8_t *d = (uint8_t *)malloc((size_t)sz);
+    if (!d || fread(d, 1, (size_t)sz, fp) != (size_t)sz) { free(d); fclose(fp); return -1; }
+    fclose(fp);
+    f->file_bytes = (uint64_t)sz;
+    int rc = -1;
+    size_t off = 0;
+    if (!memcmp(d, "ID3", 3) && sz > 10) /* skip an ID3v2 tag in front of a FLAC stream */
+        off = 10 + (((size_t)d[6] & 0x7F) << 21 | ((size_t)d[7] & 0x7F) << 14 | ((size_t)d[8] & 0x7F) << 7 | ((size_t)d[9] & 0x7F));
+    if (off + 4 < (size_t)sz && !memcmp(d + off, "fLaC", 4)) rc = decode_flac(d + off, (size_t)sz - off, f);
+    else if (!memcmp(d, "RIFF", 4) && !memcmp(d + 8, "WAVE", 4)) rc = decode_wav(d, (size_t)sz, f);
+    free(d);
+    if (rc) blx_pcm_file_free(f);
+    return rc;
+}
+
+void blx_pcm_file_free(blx_pcm_file *f) {
+    free(f->samples);
+    free(f->artist); free(f->title); free(f->album); free(f->tracknumber); free(f->genre);
+    memset(f, 0, sizeof(*f));
+}

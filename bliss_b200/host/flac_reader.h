@@ -1,0 +1,21 @@
+/* Host-side container readers (FLAC, WAV) used by bl_audio_decode. See flac_reader.c. */
+#ifndef BLX_FLAC_READER_H
+#define BLX_FLAC_READER_H
+#include <stddef.h>
+#include <stdint.h>
+
+typedef struct blx_pcm_file {
+    int32_t *samples;      /* interleaved, n_frames * channels; raw IEEE bits when is_float */
+    size_t n_frames;       /* sample frames (per channel) */
+    int channels;
+    int sample_rate;
+    int bits_per_sample;
+    int is_float;
+    uint64_t file_bytes;
+    uint8_t md5[16];       /* FLAC STREAMINFO md5 of the unencoded audio (zero for WAV) */
+    char *artist, *title, *album, *tracknumber, *genre; /* NULL when absent */
+} blx_pcm_file;
+
+int blx_pcm_file_read(const char *filename, blx_pcm_file *out); /* 0 on success */
+void blx_pcm_file_free(blx_pcm_file *f);
+#endif
