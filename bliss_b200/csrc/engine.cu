@@ -1,0 +1,692 @@
+// engine.cu — the C-ABI of blx.h: device memory, streams, batching and kernel sequencing.
+//
+// Per chunk of songs the engine enqueues
+//     memset(hist, stats, energy) -> pass1 -> epilogue -> envelope -> tail
+// on one stream. The host-buffer entry points split a batch into chunks that fit a device
+// staging buffer and alternate between two slots, so the host->device copy of chunk i+1
+// (copy stream) overlaps the kernels of chunk i (compute stream).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "blx_common.cuh"
+#include "kernels.h"
+
+using namespace blx;
+
+// ---------------------------------------------------------------- error reporting
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(BLX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *blx_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------- grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Slot {
+    DevBuf pcm, songs, partials, hist, stats, norm, energy, q, results, freq;
+    SongDesc *h_songs = nullptr; // pinned
+    size_t h_songs_cap = 0;
+    blx_result *h_results = nullptr; // pinned
+    size_t h_results_cap = 0;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool busy = false;
+    int n_songs = 0;
+    int first_song = 0; // index in the caller's batch
+};
+
+struct ProfRec {
+    int kid;
+    cudaEvent_t a, b;
+};
+
+struct blx_engine {
+    int device = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    float *d_hann = nullptr;
+    float2 *d_tw1f = nullptr, *d_tw2f = nullptr;
+    double2 *d_tw1d = nullptr, *d_tw2d = nullptr;
+    Slot slot[2];
+    int next_slot = 0;
+    size_t chunk_bytes = (size_t)1 << 30;
+    bool prof = false;
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    float prof_ms[BLX_K_COUNT] = {0};
+    int prof_n[BLX_K_COUNT] = {0};
+    long long launches = 0;
+    DevBuf scratch_a, scratch_b;
+};
+
+static const char *kKernelNames[BLX_K_COUNT] = {"pass1_kernel", "epilogue_kernel", "envelope_kernel", "tail_kernel",
+                                                "distance_kernel"};
+extern "C" const char *blx_kernel_name(int id) { return (id >= 0 && id < BLX_K_COUNT) ? kKernelNames[id] : "?"; }
+
+// ---------------------------------------------------------------- profiling helpers
+static cudaEvent_t ev_get(blx_engine *e) {
+    if (!e->ev_pool.empty()) {
+        cudaEvent_t ev = e->ev_pool.back();
+        e->ev_pool.pop_back();
+        return ev;
+    }
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    return ev;
+}
+struct ProfScope {
+    blx_engine *e;
+    int kid;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(blx_engine *e_, int kid_, cudaStream_t st_) : e(e_), kid(kid_), st(st_) {
+        e->launches++;
+        if (e->prof) {
+            a = ev_get(e);
+            b = ev_get(e);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~ProfScope() {
+        if (e->prof) {
+            cudaEventRecord(b, st);
+            e->prof_pending.push_back({kid, a, b});
+        }
+    }
+};
+
+static int prof_drain(blx_engine *e) {
+    for (auto &r : e->prof_pending) {
+        CK(cudaEventSynchronize(r.b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, r.a, r.b));
+        e->prof_ms[r.kid] += ms;
+        e->prof_n[r.kid] += 1;
+        e->ev_pool.push_back(r.a);
+        e->ev_pool.push_back(r.b);
+    }
+    e->prof_pending.clear();
+    return BLX_OK;
+}
+
+extern "C" int blx_profile_enable(blx_engine *e, int on) {
+    if (!e) return fail(BLX_ERR_ARG, "null engine");
+    e->prof = on != 0;
+    return BLX_OK;
+}
+extern "C" int blx_profile_reset(blx_engine *e) {
+    if (!e) return fail(BLX_ERR_ARG, "null engine");
+    int rc = prof_drain(e);
+    for (int i = 0; i < BLX_K_COUNT; ++i) { e->prof_ms[i] = 0; e->prof_n[i] = 0; }
+    return rc;
+}
+extern "C" int blx_profile_read(blx_engine *e, float *ms, int *launches) {
+    if (!e) return fail(BLX_ERR_ARG, "null engine");
+    int rc = prof_drain(e);
+    for (int i = 0; i < BLX_K_COUNT; ++i) {
+        if (ms) ms[i] = e->prof_ms[i];
+        if (launches) launches[i] = e->prof_n[i];
+    }
+    return rc;
+}
+extern "C" long long blx_launch_count(blx_engine *e) { return e ? e->launches : 0; }
+
+// ---------------------------------------------------------------- lifecycle
+extern "C" int blx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int blx_init(int device, blx_engine **out) {
+    if (!out) return fail(BLX_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(BLX_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU path",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+    }
+    if (device < 0 || device >= n) return fail(BLX_ERR_ARG, "device %d out of range [0, %d)", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(BLX_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major,
+                    prop.minor);
+    blx_engine *e = new blx_engine();
+    e->device = device;
+    CK(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&e->slot[i].copied, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
+    }
+    // constant tables, computed once in double on the host
+    std::vector<float> hann(kWin);
+    for (int i = 0; i < kWin; ++i) // reference src/frequency_sort.c:40-42
+        hann[i] = (float)(0.5 * (1.0 - cos(2 * M_PI * i / (kWin - 1))));
+    std::vector<float2> tw1f(256), tw2f(128);
+    std::vector<double2> tw1d(256), tw2d(128);
+    for (int c = 0; c < 16; ++c)
+        for (int b = 0; b < 16; ++b) {
+            const double a = -2.0 * M_PI * (double)((b * c) % 256) / 256.0;
+            tw1d[c * 16 + b] = make_double2(cos(a), sin(a));
+            tw1f[c * 16 + b] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int k = 0; k < 128; ++k) {
+        const double a = -2.0 * M_PI * (double)k / 512.0;
+        tw2d[k] = make_double2(cos(a), sin(a));
+        tw2f[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    CK(cudaMalloc(&e->d_hann, kWin * sizeof(float)));
+    CK(cudaMalloc(&e->d_tw1f, 256 * sizeof(float2)));
+    CK(cudaMalloc(&e->d_tw2f, 128 * sizeof(float2)));
+    CK(cudaMalloc(&e->d_tw1d, 256 * sizeof(double2)));
+    CK(cudaMalloc(&e->d_tw2d, 128 * sizeof(double2)));
+    CK(cudaMemcpy(e->d_hann, hann.data(), kWin * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_tw1f, tw1f.data(), 256 * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_tw2f, tw2f.data(), 128 * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_tw1d, tw1d.data(), 256 * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_tw2d, tw2d.data(), 128 * sizeof(double2), cudaMemcpyHostToDevice));
+    *out = e;
+    return BLX_OK;
+}
+
+extern "C" void blx_shutdown(blx_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        Slot &s = e->slot[i];
+        s.pcm.release(); s.songs.release(); s.partials.release(); s.hist.release(); s.stats.release();
+        s.norm.release(); s.energy.release(); s.q.release(); s.results.release(); s.freq.release();
+        if (s.h_songs) cudaFreeHost(s.h_songs);
+        if (s.h_results) cudaFreeHost(s.h_results);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    e->scratch_a.release();
+    e->scratch_b.release();
+    for (auto &r : e->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+    cudaFree(e->d_hann); cudaFree(e->d_tw1f); cudaFree(e->d_tw2f); cudaFree(e->d_tw1d); cudaFree(e->d_tw2d);
+    if (e->compute) cudaStreamDestroy(e->compute);
+    if (e->copy) cudaStreamDestroy(e->copy);
+    delete e;
+}
+
+extern "C" int blx_configure(blx_engine *e, size_t chunk_bytes) {
+    if (!e) return fail(BLX_ERR_ARG, "null engine");
+    if (chunk_bytes < ((size_t)1 << 20)) return fail(BLX_ERR_ARG, "chunk_bytes must be at least 1 MiB");
+    e->chunk_bytes = chunk_bytes;
+    return BLX_OK;
+}
+
+// ---------------------------------------------------------------- descriptors
+static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+struct ChunkPlan {
+    int kind = 0;
+    int max_parts = 0;
+    int parts_total = 0;
+    int max_hops = 0;
+    long long energy_total = 0;
+    long long q_total = 0;
+};
+
+// Fills n descriptors. offsets/lengths are in input elements.
+static void plan_songs(int fmt, const long long *offsets, const long long *lengths, int channels_kind,
+                       const unsigned long long *durations, int n, SongDesc *sd, ChunkPlan *plan) {
+    const int tile_m = pass1_tile_msamples();
+    // enough CTAs for ~8 waves of 3 CTAs on 148 SMs, without splitting a song finer than one tile per CTA
+    const int target_ctas = 148 * 3 * 8;
+    const int parts_wanted = std::max(1, (target_ctas + n - 1) / n);
+    plan->kind = (fmt == BLX_FMT_F32) ? kInF32 : channels_kind;
+    long long env = 0, q = 0;
+    int parts = 0;
+    for (int i = 0; i < n; ++i) {
+        SongDesc d;
+        memset(&d, 0, sizeof(d));
+        d.pcm_off = offsets[i];
+        d.kind = plan->kind;
+        d.n_elems = (int)lengths[i];
+        if (fmt == BLX_FMT_F32) {
+            d.n_msamples = (int)(lengths[i] / 2);
+            d.n_samples = 2 * d.n_msamples;
+            d.duration = (unsigned)(lengths[i] / BLX_FE_IN_RATE);
+            d.q_off = q;
+            q += round_up(std::max(d.n_msamples, 1), 64);
+        } else {
+            d.n_samples = (int)lengths[i];
+            d.n_msamples = (plan->kind == kInS16Mono) ? d.n_samples : d.n_samples / 2;
+            d.duration = durations ? (unsigned)durations[i] : 0u;
+        }
+        d.n_frames = d.n_msamples / kWin;
+        // tiles cover every input element (the histogram and the statistics need the tail too)
+        const long long rows_elems = (plan->kind == kInS16Mono) ? 32 : 64;
+        const long long rows = (d.n_elems + rows_elems - 1) / rows_elems;
+        d.n_tiles = (int)std::max(1ll, (rows * 32 + tile_m - 1) / tile_m);
+        d.F = d.n_samples / kWin;
+        d.n_hops = std::max(0, 2 * d.F - 2);
+        d.env_off = env;
+        env += round_up(std::max(2 * d.F, 2), 8);
+        d.n_parts = std::min(parts_wanted, d.n_tiles);
+        d.part_off = parts;
+        parts += d.n_parts;
+        plan->max_parts = std::max(plan->max_parts, d.n_parts);
+        plan->max_hops = std::max(plan->max_hops, d.n_hops);
+        sd[i] = d;
+    }
+    plan->parts_total = parts;
+    plan->energy_total = env;
+    plan->q_total = q;
+}
+
+// ---------------------------------------------------------------- the kernel sequence for one chunk
+static int ensure_host_songs(Slot &s, int n) {
+    if ((size_t)n > s.h_songs_cap) {
+        if (s.h_songs) cudaFreeHost(s.h_songs);
+        s.h_songs = nullptr;
+        s.h_songs_cap = 0;
+        const size_t cap = std::max<size_t>(1024, (size_t)n * 2);
+        CK(cudaMallocHost(&s.h_songs, cap * sizeof(SongDesc)));
+        s.h_songs_cap = cap;
+    }
+    if ((size_t)n > s.h_results_cap) {
+        if (s.h_results) cudaFreeHost(s.h_results);
+        s.h_results = nullptr;
+        s.h_results_cap = 0;
+        const size_t cap = std::max<size_t>(1024, (size_t)n * 2);
+        CK(cudaMallocHost(&s.h_results, cap * sizeof(blx_result)));
+        s.h_results_cap = cap;
+    }
+    return BLX_OK;
+}
+
+// Songs already described in s.h_songs[0..n). d_pcm is the packed input.
+static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *d_pcm, int n, unsigned what,
+                     blx_result *d_out, float *d_freq_only, cudaStream_t st) {
+    const bool full = (d_freq_only == nullptr);
+    CK(s.songs.reserve((size_t)n * sizeof(SongDesc)));
+    CK(s.partials.reserve((size_t)std::max(plan.parts_total, 1) * 256 * sizeof(float)));
+    CK(s.norm.reserve((size_t)n * sizeof(SongNorm)));
+    if (full) {
+        CK(s.hist.reserve((size_t)n * kHistStride * sizeof(unsigned)));
+        CK(s.stats.reserve((size_t)n * sizeof(SongStats)));
+        CK(s.energy.reserve((size_t)std::max(plan.energy_total, 8ll) * sizeof(double)));
+        if (plan.kind == kInF32) CK(s.q.reserve((size_t)std::max(plan.q_total, 64ll) * sizeof(short)));
+    }
+    CK(cudaMemcpyAsync(s.songs.p, s.h_songs, (size_t)n * sizeof(SongDesc), cudaMemcpyHostToDevice, st));
+    if (full) {
+        CK(cudaMemsetAsync(s.hist.p, 0, (size_t)n * kHistStride * sizeof(unsigned), st));
+        CK(cudaMemsetAsync(s.stats.p, 0, (size_t)n * sizeof(SongStats), st));
+        if (what & BLX_DO_ENVELOPE) CK(cudaMemsetAsync(s.energy.p, 0, (size_t)plan.energy_total * sizeof(double), st));
+    }
+    const SongDesc *d_songs = static_cast<const SongDesc *>(s.songs.p);
+    {
+        Pass1Params p;
+        p.pcm = d_pcm;
+        p.songs = d_songs;
+        p.hann = e->d_hann;
+        p.tw1 = e->d_tw1f;
+        p.tw2 = e->d_tw2f;
+        p.partials = static_cast<float *>(s.partials.p);
+        p.hist = static_cast<unsigned *>(s.hist.p);
+        p.stats = static_cast<SongStats *>(s.stats.p);
+        p.qout = static_cast<short *>(s.q.p);
+        ProfScope ps(e, BLX_K_PASS1, st);
+        CK(launch_pass1(plan.kind, full, p, plan.max_parts, n, st));
+    }
+    {
+        EpilogueParams p;
+        p.songs = d_songs;
+        p.partials = static_cast<const float *>(s.partials.p);
+        p.hist = static_cast<const unsigned *>(s.hist.p);
+        p.stats = full ? static_cast<const SongStats *>(s.stats.p) : nullptr;
+        p.norm = static_cast<SongNorm *>(s.norm.p);
+        p.frequency = d_freq_only;
+        p.what = full ? what : BLX_DO_FREQUENCY;
+        ProfScope ps(e, BLX_K_EPILOGUE, st);
+        CK(launch_epilogue(p, n, st));
+    }
+    if (!full) return BLX_OK;
+    if (what & BLX_DO_ENVELOPE) {
+        EnvelopeParams p;
+        p.stream = (plan.kind == kInF32) ? static_cast<const short *>(s.q.p) : static_cast<const short *>(d_pcm);
+        p.songs = d_songs;
+        p.norm = static_cast<const SongNorm *>(s.norm.p);
+        p.tw1 = e->d_tw1d;
+        p.tw2 = e->d_tw2d;
+        p.energy = static_cast<double *>(s.energy.p);
+        p.dup = (plan.kind == kInF32) ? 1 : 0;
+        ProfScope ps(e, BLX_K_ENVELOPE, st);
+        CK(launch_envelope(p, plan.max_hops, n, st));
+    }
+    {
+        TailParams p;
+        p.songs = d_songs;
+        p.norm = static_cast<const SongNorm *>(s.norm.p);
+        p.energy = static_cast<const double *>(s.energy.p);
+        p.out = d_out;
+        p.what = what;
+        ProfScope ps(e, BLX_K_TAIL, st);
+        CK(launch_tail(p, n, st));
+    }
+    return BLX_OK;
+}
+
+static int check_engine(blx_engine *e) {
+    if (!e) return fail(BLX_ERR_ARG, "null engine (blx_init failed or was not called)");
+    CK(cudaSetDevice(e->device));
+    return BLX_OK;
+}
+
+// ---------------------------------------------------------------- device-resident entry points
+static int analyze_device_impl(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets, const int64_t *lengths,
+                               const int *channels, const uint64_t *duration_s, int n_songs, unsigned what,
+                               blx_result *d_out, float *d_freq_only, void *stream) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (n_songs <= 0) return BLX_OK;
+    if (!d_pcm || !offsets || !lengths) return fail(BLX_ERR_ARG, "null input array");
+    if (fmt != BLX_FMT_S16 && fmt != BLX_FMT_F32) return fail(BLX_ERR_ARG, "unknown format %d", fmt);
+    if (!(what & BLX_DO_ALL)) return fail(BLX_ERR_ARG, "empty analyser mask");
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->compute;
+    // songs are processed in runs of equal channel count, at most 65535 per launch (gridDim.y)
+    int i0 = 0;
+    while (i0 < n_songs) {
+        const int ch0 = (fmt == BLX_FMT_S16 && channels) ? channels[i0] : 2;
+        int i1 = i0;
+        while (i1 < n_songs && i1 - i0 < 65535 && ((fmt == BLX_FMT_S16 && channels) ? channels[i1] : 2) == ch0) ++i1;
+        if (fmt == BLX_FMT_S16 && ch0 != 1 && ch0 != 2) return fail(BLX_ERR_ARG, "song %d: %d channels unsupported", i0, ch0);
+        const int n = i1 - i0;
+        Slot &s = e->slot[e->next_slot];
+        e->next_slot ^= 1;
+        if (s.busy) {
+            CK(cudaEventSynchronize(s.done));
+            s.busy = false;
+        }
+        rc = ensure_host_songs(s, n);
+        if (rc) return rc;
+        for (int i = i0; i < i1; ++i) {
+            if (offsets[i] % BLX_ALIGN_ELEMS) return fail(BLX_ERR_ARG, "song %d: offset not a multiple of %d", i, BLX_ALIGN_ELEMS);
+            if (lengths[i] < 0 || lengths[i] > 0x7fffffffll) return fail(BLX_ERR_ARG, "song %d: bad length", i);
+        }
+        ChunkPlan plan;
+        plan_songs(fmt, reinterpret_cast<const long long *>(offsets + i0), reinterpret_cast<const long long *>(lengths + i0),
+                   ch0 == 1 ? kInS16Mono : kInS16Stereo,
+                   duration_s ? reinterpret_cast<const unsigned long long *>(duration_s + i0) : nullptr, n, s.h_songs, &plan);
+        rc = run_chunk(e, s, plan, d_pcm, n, what, d_out ? d_out + i0 : nullptr, d_freq_only ? d_freq_only + i0 : nullptr, st);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.done, st));
+        s.busy = true;
+        i0 = i1;
+    }
+    return BLX_OK;
+}
+
+extern "C" int blx_analyze_device(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets, const int64_t *lengths,
+                                  const int *channels, const uint64_t *duration_s, int n_songs, unsigned what,
+                                  blx_result *d_out, void *stream) {
+    if (!d_out) return fail(BLX_ERR_ARG, "null d_out");
+    return analyze_device_impl(e, fmt, d_pcm, offsets, lengths, channels, duration_s, n_songs, what, d_out, nullptr, stream);
+}
+
+extern "C" int blx_spectral_device(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets, const int64_t *lengths,
+                                   const int *channels, int n_songs, float *d_frequency, void *stream) {
+    if (!d_frequency) return fail(BLX_ERR_ARG, "null d_frequency");
+    return analyze_device_impl(e, fmt, d_pcm, offsets, lengths, channels, nullptr, n_songs, BLX_DO_FREQUENCY, nullptr,
+                               d_frequency, stream);
+}
+
+// ---------------------------------------------------------------- host-buffer entry points
+template <typename T>
+static int analyze_host_impl(blx_engine *e, int fmt, const T *const *pcm, const long long *lengths, const int *channels,
+                             const uint64_t *duration_s, int n_songs, unsigned what, blx_result *out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (n_songs <= 0) return BLX_OK;
+    if (!pcm || !lengths || !out) return fail(BLX_ERR_ARG, "null input array");
+    if (!(what & BLX_DO_ALL)) return fail(BLX_ERR_ARG, "empty analyser mask");
+    const size_t cap_elems = e->chunk_bytes / sizeof(T);
+    std::vector<long long> offs;
+    int i0 = 0;
+    int pending[2] = {-1, -1}; // first song of the chunk in flight in each slot
+    int pending_n[2] = {0, 0};
+    auto collect = [&](int si) -> int {
+        Slot &s = e->slot[si];
+        if (pending[si] >= 0) {
+            CK(cudaEventSynchronize(s.done));
+            memcpy(out + pending[si], s.h_results, (size_t)pending_n[si] * sizeof(blx_result));
+            pending[si] = -1;
+            s.busy = false;
+        }
+        return BLX_OK;
+    };
+    while (i0 < n_songs) {
+        const int ch0 = (fmt == BLX_FMT_S16 && channels) ? channels[i0] : 2;
+        if (fmt == BLX_FMT_S16 && ch0 != 1 && ch0 != 2) return fail(BLX_ERR_ARG, "song %d: %d channels unsupported", i0, ch0);
+        // greedy chunk: equal channel count, fits the staging buffer (a single oversized song grows it)
+        offs.clear();
+        long long used = 0;
+        int i1 = i0;
+        while (i1 < n_songs && i1 - i0 < 65535) {
+            const int ch = (fmt == BLX_FMT_S16 && channels) ? channels[i1] : 2;
+            if (ch != ch0) break;
+            if (lengths[i1] < 0 || lengths[i1] > 0x7fffffffll || !pcm[i1]) return fail(BLX_ERR_ARG, "song %d: bad buffer", i1);
+            const long long need = round_up(std::max(lengths[i1], 1ll), BLX_ALIGN_ELEMS) + BLX_ALIGN_ELEMS;
+            if (i1 > i0 && (size_t)(used + need) > cap_elems) break;
+            offs.push_back(used);
+            used += need;
+            ++i1;
+        }
+        const int n = i1 - i0;
+        const int si = e->next_slot;
+        e->next_slot ^= 1;
+        rc = collect(si);
+        if (rc) return rc;
+        Slot &s = e->slot[si];
+        if (s.busy) { CK(cudaEventSynchronize(s.done)); s.busy = false; }
+        CK(s.pcm.reserve((size_t)used * sizeof(T)));
+        rc = ensure_host_songs(s, n);
+        if (rc) return rc;
+        CK(s.results.reserve((size_t)n * sizeof(blx_result)));
+        for (int i = 0; i < n; ++i)
+            CK(cudaMemcpyAsync(static_cast<T *>(s.pcm.p) + offs[i], pcm[i0 + i], (size_t)lengths[i0 + i] * sizeof(T),
+                               cudaMemcpyHostToDevice, e->copy));
+        CK(cudaEventRecord(s.copied, e->copy));
+        CK(cudaStreamWaitEvent(e->compute, s.copied, 0));
+        ChunkPlan plan;
+        plan_songs(fmt, offs.data(), lengths + i0, ch0 == 1 ? kInS16Mono : kInS16Stereo,
+                   duration_s ? reinterpret_cast<const unsigned long long *>(duration_s + i0) : nullptr, n, s.h_songs, &plan);
+        rc = run_chunk(e, s, plan, s.pcm.p, n, what, static_cast<blx_result *>(s.results.p), nullptr, e->compute);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(s.h_results, s.results.p, (size_t)n * sizeof(blx_result), cudaMemcpyDeviceToHost, e->compute));
+        CK(cudaEventRecord(s.done, e->compute));
+        s.busy = true;
+        pending[si] = i0;
+        pending_n[si] = n;
+        i0 = i1;
+    }
+    rc = collect(e->next_slot);
+    if (rc) return rc;
+    rc = collect(e->next_slot ^ 1);
+    return rc;
+}
+
+extern "C" int blx_analyze_batch_s16(blx_engine *e, const int16_t *const *pcm, const int *n_samples, const int *channels,
+                                     const uint64_t *duration_s, int n_songs, unsigned what, blx_result *out) {
+    if (n_songs > 0 && !n_samples) return fail(BLX_ERR_ARG, "null n_samples");
+    std::vector<long long> len(n_songs > 0 ? n_songs : 0);
+    for (int i = 0; i < n_songs; ++i) len[i] = n_samples[i];
+    return analyze_host_impl<int16_t>(e, BLX_FMT_S16, pcm, len.data(), channels, duration_s, n_songs, what, out);
+}
+
+extern "C" int blx_analyze_batch_f32(blx_engine *e, const float *const *pcm, const int64_t *n_in, int n_songs, unsigned what,
+                                     blx_result *out) {
+    if (n_songs > 0 && !n_in) return fail(BLX_ERR_ARG, "null n_in");
+    return analyze_host_impl<float>(e, BLX_FMT_F32, pcm, reinterpret_cast<const long long *>(n_in), nullptr, nullptr, n_songs,
+                                    what, out);
+}
+
+// ---------------------------------------------------------------- distances
+extern "C" int blx_distance_rows_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows, int mode,
+                                        float *d_out, void *stream) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!d_vectors || !d_out || n < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n || (mode != 0 && mode != 1))
+        return fail(BLX_ERR_ARG, "bad distance arguments");
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->compute;
+    ProfScope ps(e, BLX_K_DISTANCE, st);
+    CK(launch_distance_rows(d_vectors, n, row0, n_rows, mode, d_out, st));
+    return BLX_OK;
+}
+
+extern "C" int blx_distance_nearest_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows,
+                                           int *d_nearest_index, float *d_nearest_dist, double *d_row_sum, void *stream) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!d_vectors || n < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n) return fail(BLX_ERR_ARG, "bad distance arguments");
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->compute;
+    ProfScope ps(e, BLX_K_DISTANCE, st);
+    CK(launch_distance_nearest(d_vectors, n, row0, n_rows, d_nearest_index, d_nearest_dist, d_row_sum, st));
+    return BLX_OK;
+}
+
+static int matrix_host(blx_engine *e, const float *vectors, int n, float *out, int mode) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (n <= 0) return BLX_OK;
+    if (!vectors || !out) return fail(BLX_ERR_ARG, "null array");
+    CK(e->scratch_a.reserve((size_t)n * 16));
+    CK(cudaMemcpyAsync(e->scratch_a.p, vectors, (size_t)n * 16, cudaMemcpyHostToDevice, e->compute));
+    // slabs of at most 256 MiB of output
+    const int rows_per = (int)std::max<long long>(1, std::min<long long>(n, ((long long)256 << 20) / ((long long)n * 4)));
+    CK(e->scratch_b.reserve((size_t)rows_per * n * 4));
+    for (int r0 = 0; r0 < n; r0 += rows_per) {
+        const int nr = std::min(rows_per, n - r0);
+        rc = blx_distance_rows_device(e, static_cast<const float *>(e->scratch_a.p), n, r0, nr, mode,
+                                      static_cast<float *>(e->scratch_b.p), nullptr);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out + (size_t)r0 * n, e->scratch_b.p, (size_t)nr * n * 4, cudaMemcpyDeviceToHost, e->compute));
+        CK(cudaStreamSynchronize(e->compute));
+    }
+    return BLX_OK;
+}
+extern "C" int blx_distance_matrix(blx_engine *e, const float *vectors, int n, float *out) { return matrix_host(e, vectors, n, out, 0); }
+extern "C" int blx_cosine_matrix(blx_engine *e, const float *vectors, int n, float *out) { return matrix_host(e, vectors, n, out, 1); }
+
+// ---------------------------------------------------------------- small helpers
+extern "C" int blx_rectangular_filter(blx_engine *e, double *out, const double *in, int n, int width) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!out || !in || width <= 0 || n < width) return fail(BLX_ERR_ARG, "bad filter arguments");
+    CK(e->scratch_a.reserve((size_t)n * 8));
+    CK(e->scratch_b.reserve((size_t)n * 8));
+    CK(cudaMemcpyAsync(e->scratch_a.p, in, (size_t)n * 8, cudaMemcpyHostToDevice, e->compute));
+    CK(cudaMemcpyAsync(e->scratch_b.p, out, (size_t)n * 8, cudaMemcpyHostToDevice, e->compute));
+    e->launches++;
+    CK(launch_rect_filter(static_cast<double *>(e->scratch_b.p), static_cast<const double *>(e->scratch_a.p), n, width, e->compute));
+    CK(cudaMemcpyAsync(out, e->scratch_b.p, (size_t)n * 8, cudaMemcpyDeviceToHost, e->compute));
+    CK(cudaStreamSynchronize(e->compute));
+    return BLX_OK;
+}
+
+extern "C" int blx_frontend_f32(blx_engine *e, const float *pcm, int64_t n_in, int16_t *out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!pcm || !out || n_in < 2) return fail(BLX_ERR_ARG, "bad front-end arguments");
+    CK(e->scratch_a.reserve((size_t)n_in * 4));
+    CK(e->scratch_b.reserve((size_t)(n_in / 2) * 4));
+    CK(cudaMemcpyAsync(e->scratch_a.p, pcm, (size_t)n_in * 4, cudaMemcpyHostToDevice, e->compute));
+    e->launches++;
+    CK(launch_frontend(static_cast<const float *>(e->scratch_a.p), n_in, static_cast<short *>(e->scratch_b.p), e->compute));
+    CK(cudaMemcpyAsync(out, e->scratch_b.p, (size_t)(n_in / 2) * 4, cudaMemcpyDeviceToHost, e->compute));
+    CK(cudaStreamSynchronize(e->compute));
+    return BLX_OK;
+}
+
+// Runs the full sequence on one S16 stereo song and leaves the intermediates in slot 0.
+static int one_song_s16(blx_engine *e, const int16_t *pcm, int n_samples, uint64_t duration, unsigned what, blx_result *res) {
+    const int16_t *ptrs[1] = {pcm};
+    const int ns[1] = {n_samples};
+    const uint64_t du[1] = {duration};
+    e->next_slot = 0;
+    return blx_analyze_batch_s16(e, ptrs, ns, nullptr, du, 1, what, res);
+}
+
+extern "C" int blx_mean_variance_s16(blx_engine *e, const int16_t *pcm, int n_samples, const int *mean_in, int *mean,
+                                     int *variance) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!pcm || n_samples <= 0) return fail(BLX_ERR_ARG, "bad arguments");
+    blx_result r;
+    rc = one_song_s16(e, pcm, n_samples, 1, BLX_DO_ALL, &r);
+    if (rc) return rc;
+    SongNorm nm;
+    SongStats st;
+    CK(cudaMemcpy(&nm, e->slot[0].norm.p, sizeof(nm), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, e->slot[0].stats.p, sizeof(st), cudaMemcpyDeviceToHost));
+    if (mean) *mean = nm.mean;
+    if (variance) {
+        if (!mean_in || *mean_in == nm.mean) {
+            *variance = nm.variance;
+        } else { // same integer identity as the epilogue kernel, around the caller's mean
+            const long long m = *mean_in;
+            const long long dev = (long long)st.sumsq - 2ll * m * st.sum + (long long)n_samples * m * m;
+            *variance = (int)(dev / n_samples);
+        }
+    }
+    return BLX_OK;
+}
+
+extern "C" int blx_envelope_energy_s16(blx_engine *e, const int16_t *pcm, int n_samples, double *energy) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!pcm || n_samples <= 0 || !energy) return fail(BLX_ERR_ARG, "bad arguments");
+    blx_result r;
+    rc = one_song_s16(e, pcm, n_samples, 1, BLX_DO_ALL, &r);
+    if (rc) return rc;
+    const int nb = 2 * (n_samples / kWin);
+    if (nb > 0) CK(cudaMemcpy(energy, e->slot[0].energy.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost));
+    return BLX_OK;
+}

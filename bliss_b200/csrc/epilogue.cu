@@ -1,0 +1,336 @@
+// epilogue.cu — the per-song scalar stages, in the reference's operation order.
+// Compiled with -fmad=false: the reference is built -std=c99 (no FMA contraction, reference
+// CMakeLists.txt:22), and everything here is latency- not throughput-bound.
+//
+//   epilogue_kernel (BLX_K_EPILOGUE), one CTA per song:
+//     - sums the song's partial spectra in a fixed order, then steps 6-9 of the frequency rating
+//       (reference src/frequency_sort.c:97-139);
+//     - 301 passes of the 7-tap [1,3,6,7,6,3,1]/27 smoothing on the 3807 histogram bins that can
+//       reach the integration window, with the reference's float/double rounding sequence, then
+//       normalisation and the window integral (reference src/amplitude_sort.c:41-79). Bit-exact
+//       with the reference for the same histogram;
+//     - bl_mean / bl_variance from the integer sums (reference src/helpers.c:30-49) and the
+//       normalisation constants of reference src/tempo_atk_sort.c:105-107.
+//   tail_kernel (BLX_K_TAIL), one thread per song: reference src/tempo_atk_sort.c:184-287 as a single
+//     streaming pass (log compression, x2 zero-stuffing, 6th-order IIR, rectified difference, weighted
+//     mix, two width-19 running-sum filters with their edge quirks, onset count) + the rating of
+//     reference src/analyze.c:63-79.
+//   rect_filter_kernel: bl_rectangular_filter (reference src/tempo_atk_sort.c:19-40) for the public
+//     helper of bliss.h.
+#include <math.h>
+
+#include "blx_common.cuh"
+#include "kernels.h"
+
+namespace blx {
+
+namespace {
+constexpr int kEpThreads = 256;
+constexpr int kSmW = kHistBins + 6; // 3 zero bins of padding on each side
+
+__device__ __forceinline__ float block_max(float v, float *scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = scratch[0];
+    for (int i = 1; i < kEpThreads / 32; ++i) r = fmaxf(r, scratch[i]);
+    __syncthreads();
+    return r;
+}
+} // namespace
+
+__global__ void __launch_bounds__(kEpThreads) epilogue_kernel(EpilogueParams p) {
+    __shared__ float ps[257];
+    __shared__ float hA[kSmW], hB[kSmW];
+    __shared__ float scratch[8];
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x;
+    const SongDesc sd = p.songs[s];
+    SongNorm out;
+    out.mean_d = 0.0; out.inv_var_d = 0.0; out.amplitude = 0.0f; out.frequency = 0.0f; out.status = 0;
+    out.mean = 0; out.variance = 0; out.pad = 0;
+
+    // ------------------------------------------------------------ frequency (A.1 steps 6-9)
+    if (p.what & BLX_DO_FREQUENCY) {
+        float acc = 0.0f;
+        if (tid >= 1) // bins 1..255; ps[256] stays 0 (Nyquist ignored, reference src/frequency_sort.c:58-62,88)
+            for (int q = 0; q < sd.n_parts; ++q) acc += p.partials[(size_t)(sd.part_off + q) * 256 + tid];
+        // d = tid (1..255) and d = 256 handled by thread 0
+        const int d = (tid == 0) ? 256 : tid;
+        float v = (float)sqrt((double)(acc / 512.0f));
+        const float peak = block_max(v, scratch);
+        v = (float)(20 * log10((double)(v / peak)) - 3);
+        ps[d] = v;
+        __syncthreads();
+        if (tid == 0) {
+            float b0 = (ps[2] + ps[4]) / 2;
+            float b1 = (ps[6] + ps[8]) / 2;
+            float b2 = 0.0f, b3 = 0.0f, b4 = 0.0f;
+            for (int i = 10; i <= 60; ++i) b2 += ps[i];
+            b2 /= 50;
+            for (int i = 61; i <= 118; ++i) b3 += ps[i];
+            b3 /= 57;
+            for (int i = 119; i <= 234; ++i) b4 += ps[i];
+            b4 /= 115;
+            const float bands_sum = b4 + b3 + b2 - b0 - b1;
+            out.frequency = (float)((1. / 3.) * (double)bands_sum + 68. / 3.);
+        }
+    }
+
+    // ------------------------------------------------------------ amplitude (A.2 steps 3-5)
+    const SongStats st = p.stats ? p.stats[s] : SongStats{0, 0ull, 0u, 0u};
+    const int first_nz = (int)(0x7fffffffu - st.first_inv), last_nz = (int)st.last_p1 - 1;
+    if (p.what & BLX_DO_AMPLITUDE) {
+        if (last_nz < 0) {
+            out.status |= BLX_SONG_SILENT;
+            out.amplitude = nanf("");
+        } else {
+            const unsigned *gh = p.hist + (size_t)s * kHistStride;
+            for (int i = tid; i < kSmW; i += kEpThreads) {
+                const int b = i - 3;
+                hA[i] = (b >= 0 && b < kHistBins) ? (float)gh[b] : 0.0f;
+                hB[i] = 0.0f;
+            }
+            __syncthreads();
+            float *h = hA, *sm = hB;
+            for (int g = 0; g < kSmoothPasses; ++g) {
+                for (int i = 3 + tid; i < 3 + kHistBins; i += kEpThreads) {
+                    const float taps = h[i - 3] + (3 * h[i - 2]) + (6 * h[i - 1]) + (7 * h[i]) + (6 * h[i + 1]) +
+                                       (3 * h[i + 2]) + h[i + 3];
+                    sm[i] = (float)(1. / 27. * (double)taps);
+                }
+                __syncthreads();
+                float *t = h; h = sm; sm = t; // h now holds this pass's output (reference copies it back)
+            }
+            // h = histogram_smooth after the last pass; normalise + integrate in index order
+            if (tid == 0) {
+                const float span = (float)(first_nz - last_nz);
+                float integral = 0.0f;
+                for (int b = kIntLo; b <= kIntHi; ++b) {
+                    float v = h[b - kHistLo + 3] / span;
+                    v = (float)((double)v * 100.);
+                    v = fabsf(v);
+                    integral += v;
+                }
+                out.amplitude = -0.2f * integral + 6.0f;
+            }
+        }
+    }
+
+    // ------------------------------------------------------------ statistics (A.3 step 1-2)
+    if (tid == 0) {
+        if (p.what & BLX_DO_ENVELOPE) {
+            const int n = sd.n_samples;
+            if (n < 3 * kWin || sd.duration == 0 || 4 * sd.F < 40) out.status |= BLX_SONG_TOO_SHORT;
+            if (last_nz < 0) out.status |= BLX_SONG_SILENT;
+            if (n > 0) {
+                // `int` accumulator of the reference wraps modulo 2^32 in practice (UB in C)
+                const int mean = (int)(unsigned)(unsigned long long)st.sum / n;
+                // sum (s - m)^2 = sum s^2 - 2 m sum s + n m^2, exact in 64-bit integers
+                const long long dev = (long long)st.sumsq - 2ll * mean * st.sum + (long long)n * mean * mean;
+                const int var = (int)(dev / n);
+                if (var == 0) out.status |= BLX_SONG_FLAT;
+                out.mean = mean;
+                out.variance = var;
+                out.mean_d = (double)mean / 32768;
+                double var_d = (double)var / 32768;
+                var_d /= 32768;
+                out.inv_var_d = 1.0 / var_d;
+            }
+        }
+        p.norm[s] = out;
+        if (p.frequency) p.frequency[s] = out.frequency;
+    }
+}
+
+cudaError_t launch_epilogue(const EpilogueParams &p, int n_songs, cudaStream_t st) {
+    epilogue_kernel<<<n_songs, kEpThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// tail
+// =====================================================================================
+namespace {
+constexpr int kTailThreads = 32;
+constexpr int kBox = 19;
+
+// reference include/bandpass_coeffs.h:484-492 (data literals)
+__constant__ double c_lp_b[7] = {1.9510e-05, 1.1706e-04, 2.9266e-04, 3.9021e-04, 2.9266e-04, 1.1706e-04, 1.9510e-05};
+__constant__ double c_lp_a[7] = {1.00000, -4.59007, 8.91034, -9.34191, 5.56998, -1.78845, 0.24136};
+
+struct PeakCounter { // onsets of reference src/tempo_atk_sort.c:277-280, fed one sample at a time
+    double prev2, prev1;
+    int index_next; // index of the next sample to be pushed
+    int beat;
+    int n2;
+    double eps;
+    __device__ void push(double s) {
+        // centre = index_next - 1, valid for 1 <= centre <= n2 - 2
+        const int centre = index_next - 1;
+        if (centre >= 1 && centre <= n2 - 2)
+            if (((prev1 - prev2) > eps) && ((prev1 - s) > eps)) beat++;
+        prev2 = prev1;
+        prev1 = s;
+        index_next++;
+    }
+};
+} // namespace
+
+__global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_songs) {
+    __shared__ double ring1[kBox][kTailThreads]; // last 19 inputs of the first box filter (ss)
+    __shared__ double ring2[kBox][kTailThreads]; // last 19 inputs of the second box filter
+    const int s = blockIdx.x * kTailThreads + threadIdx.x;
+    if (s >= n_songs) return;
+    const int tx = threadIdx.x;
+    const SongDesc sd = p.songs[s];
+    const SongNorm nm = p.norm[s];
+    blx_result res;
+    res.tempo = 0.0f; res.attack = 0.0f; res.amplitude = nm.amplitude; res.frequency = nm.frequency;
+    res.force = 0.0f; res.calm_or_loud = 2; res.beat = 0; res.status = nm.status;
+
+    if ((p.what & BLX_DO_ENVELOPE) && nm.status == 0) {
+        const double *E = p.energy + sd.env_off;
+        const int nb = 2 * sd.F;
+        const int n2 = 2 * nb;
+        const float mu = 100.0f;
+        const float lambda = 0.8f;
+        const double log_den = log((double)(1 + mu));
+        const double w_lp = (double)(1 - lambda);
+        const double w_df = (double)(lambda * 172);
+        const double eps = (double)0.000001f;
+
+        double x1 = 0, x2 = 0, x3 = 0, x4 = 0, x5 = 0, x6 = 0; // t1 history
+        double y1 = 0, y2 = 0, y3 = 0, y4 = 0, y5 = 0, y6 = 0; // t2 history
+        double atk_sum = 0;
+        double ts1 = 0, ts2 = 0;
+        double wa_last = 0;
+        int r1 = 0, r2 = 0; // ring write positions (= index mod 19)
+        PeakCounter pk;
+        pk.prev2 = 0; pk.prev1 = 0; pk.index_next = 9; pk.beat = 0; pk.n2 = n2; pk.eps = eps;
+        // out2[0..8] = 0: the counter starts as if samples 0..8 (all zero) had been pushed.
+
+        // consume one input of the second box filter, in index order p2 = 0, 1, 2, ...
+        int p2 = 0;
+        auto feed2 = [&](double v) {
+            if (p2 < kBox) {
+                ts2 += v;
+            } else {
+                pk.push(ts2 / kBox); // out2[p2 - 10]
+                ts2 -= ring2[r2][tx]; // in2[p2 - 19]
+                ts2 += v;
+            }
+            ring2[r2][tx] = v;
+            r2 = (r2 + 1 == kBox) ? 0 : r2 + 1;
+            p2++;
+        };
+
+        for (int j = 0; j < n2; ++j) {
+            // step 6: log compression, zero-stuffed x2 (reference src/tempo_atk_sort.c:186-190)
+            const double x0 = (j & 1) ? 0.0 : log(1 + (double)mu * E[j >> 1]) / log_den;
+            // step 7: IIR (reference src/tempo_atk_sort.c:201-218)
+            double d = 0, c = 0;
+            d += c_lp_b[0] * x0; d += c_lp_b[1] * x1; d += c_lp_b[2] * x2; d += c_lp_b[3] * x3;
+            d += c_lp_b[4] * x4; d += c_lp_b[5] * x5; d += c_lp_b[6] * x6;
+            c += c_lp_a[1] * y1; c += c_lp_a[2] * y2; c += c_lp_a[3] * y3;
+            c += c_lp_a[4] * y4; c += c_lp_a[5] * y5; c += c_lp_a[6] * y6;
+            const double y = (d - c) / c_lp_a[0];
+            // step 8: rectified difference (reference src/tempo_atk_sort.c:221-226)
+            double df;
+            if (j == 0) df = y;
+            else { df = y - y1; df = (df > 0) ? df : 0; }
+            // step 9: weighted mix (reference src/tempo_atk_sort.c:229-232)
+            const double wa = w_lp * y + w_df * df / 10;
+            x6 = x5; x5 = x4; x4 = x3; x3 = x2; x2 = x1; x1 = x0;
+            y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
+            // step 10: attack sum and the ss array (reference src/tempo_atk_sort.c:246-263)
+            double in1;
+            if (j < n2 - 1) { atk_sum += wa; in1 = wa; }
+            else { in1 = 0; wa_last = wa; }
+            // step 11a: first running-sum filter (out = wa array, in = ss)
+            if (j < kBox) {
+                ts1 += in1;
+            } else {
+                // k = j - 19: out1[k + 9] = ts1 (then /19) is the next input of filter 2 at index j - 10
+            }
+            if (j >= 10) {
+                const int q = j - 10; // index of the filter-1 output becoming final now
+                double o1;
+                if (q <= 8) o1 = ring1[(q % kBox)][tx] / kBox; // untouched entries keep wa[q], then /19
+                else o1 = ts1 / kBox;                          // value before this step's update
+                feed2(o1);
+            }
+            if (j >= kBox) {
+                ts1 -= ring1[r1][tx]; // in1[j - 19]
+                ts1 += in1;
+            }
+            ring1[r1][tx] = in1;
+            r1 = (r1 + 1 == kBox) ? 0 : r1 + 1;
+        }
+        // ---- end quirks of filter 1 (reference src/tempo_atk_sort.c:34-39): indices n2-10 .. n2-1
+        {
+            // ring1 holds in1[n2-19 .. n2-1]; the oldest is at r1
+            double o = ring1[(r1 + 9) % kBox][tx]; // wa[n2 - 10] (== in1 there)
+            for (int k = 0; k < kBox; ++k) o += ring1[(r1 + k) % kBox][tx];
+            feed2(o / kBox);
+            for (int q = n2 - 9; q < n2; ++q) {
+                const double w = (q == n2 - 1) ? wa_last : ring1[(r1 + (q - (n2 - kBox))) % kBox][tx];
+                feed2(w / kBox);
+            }
+        }
+        // ---- end quirks of filter 2: out2[n2 - 10] = sum of the last 19 inputs, the rest stay 0
+        {
+            double o = 0;
+            for (int k = 0; k < kBox; ++k) o += ring2[(r2 + k) % kBox][tx];
+            pk.push(o / kBox);
+            for (int q = n2 - 9; q < n2; ++q) pk.push(0.0);
+        }
+        res.beat = pk.beat;
+        // step 13 (reference src/tempo_atk_sort.c:283-287)
+        const double tempo_score = (double)(4 * (float)pk.beat / (float)sd.duration) - 30.4;
+        const double atk_score = -1.74 * atk_sum * 10000 / sd.n_samples + 58.3;
+        res.tempo = (float)tempo_score;
+        res.attack = (float)atk_score;
+    } else if (p.what & BLX_DO_ENVELOPE) {
+        res.tempo = nanf("");
+        res.attack = nanf("");
+    }
+
+    if (p.what == BLX_DO_ALL) { // reference src/analyze.c:68-79
+        const float rating = (float)(fmax((double)res.tempo, 0.0) + (double)res.amplitude + (double)res.frequency +
+                                     fmax((double)res.attack, 0.0));
+        res.force = rating;
+        res.calm_or_loud = (rating > 0) ? 0 : (rating < 0) ? 1 : 2;
+    }
+    p.out[s] = res;
+}
+
+cudaError_t launch_tail(const TailParams &p, int n_songs, cudaStream_t st) {
+    tail_kernel<<<(n_songs + kTailThreads - 1) / kTailThreads, kTailThreads, 0, st>>>(p, n_songs);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// bl_rectangular_filter helper (sequential by definition: running sum)
+// =====================================================================================
+__global__ void rect_filter_kernel(double *out, const double *in, int n, int width) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int half = (int)round(width / 2.);
+    double run = 0;
+    for (int k = 0; k < width; ++k) run += in[k];
+    for (int k = 0; k < n - width; ++k) {
+        out[k + half - 1] = run;
+        run -= in[k];
+        run += in[k + width];
+    }
+    for (int k = n - width; k < n; ++k) out[n - half] += in[k];
+    for (int k = 0; k < n; ++k) out[k] /= width;
+}
+
+cudaError_t launch_rect_filter(double *d_out, const double *d_in, int n, int width, cudaStream_t st) {
+    rect_filter_kernel<<<1, 32, 0, st>>>(d_out, d_in, n, width);
+    return cudaGetLastError();
+}
+
+} // namespace blx

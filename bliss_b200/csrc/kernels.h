@@ -1,0 +1,59 @@
+// kernels.h — launch interfaces between the engine (engine.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "blx_common.cuh"
+
+namespace blx {
+
+struct Pass1Params {
+    const void *pcm;        // packed input buffer (int16 or float)
+    const SongDesc *songs;  // descriptors of the songs of this launch (blockIdx.y)
+    const float *hann;      // [512]
+    const float2 *tw1;      // [256] exp(-2 pi i b c / 256) at [c * 16 + b]
+    const float2 *tw2;      // [128] exp(-2 pi i k / 512)
+    float *partials;        // [n_parts_total][256]
+    unsigned *hist;         // [n_songs][kHistStride]   (FULL)
+    SongStats *stats;       // [n_songs]                (FULL)
+    short *qout;            // decimated int16 stream   (FULL, F32 input)
+};
+cudaError_t launch_pass1(int kind, bool full, const Pass1Params &p, int max_parts, int n_songs, cudaStream_t st);
+int pass1_tile_msamples();
+
+struct EpilogueParams {
+    const SongDesc *songs;
+    const float *partials;
+    const unsigned *hist;
+    const SongStats *stats;
+    SongNorm *norm;     // out
+    float *frequency;   // optional out (spectral-only entry point), may be NULL
+    unsigned what;      // BLX_DO_* mask
+};
+cudaError_t launch_epilogue(const EpilogueParams &p, int n_songs, cudaStream_t st);
+
+struct EnvelopeParams {
+    const short *stream;     // int16 samples: the S16 input itself, or the decimated stream (dup = 1)
+    const SongDesc *songs;
+    const SongNorm *norm;
+    const double2 *tw1;      // [256] double twiddles, same layout as the float ones
+    const double2 *tw2;      // [128]
+    double *energy;          // rows of 2F doubles at SongDesc::env_off: E[m]
+    int dup;                 // 1: logical S[i] = stream[q_off + (i >> 1)]; 0: S[i] = stream[pcm_off + i]
+};
+cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, cudaStream_t st);
+
+struct TailParams {
+    const SongDesc *songs;
+    const SongNorm *norm;
+    const double *energy;
+    blx_result *out;
+    unsigned what;
+};
+cudaError_t launch_tail(const TailParams &p, int n_songs, cudaStream_t st);
+
+cudaError_t launch_distance_rows(const float *d_vectors, int n, int row0, int n_rows, int mode, float *d_out, cudaStream_t st);
+cudaError_t launch_distance_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_dist,
+                                    double *d_sum, cudaStream_t st);
+cudaError_t launch_rect_filter(double *d_out, const double *d_in, int n, int width, cudaStream_t st);
+cudaError_t launch_frontend(const float *d_in, long long n_in, short *d_out, cudaStream_t st);
+
+} // namespace blx

@@ -1,0 +1,415 @@
+// pass1.cu — the streaming first pass over a song's PCM (kernel id BLX_K_PASS1).
+//
+// One launch covers a batch of songs. A CTA (128 threads) owns one (song, part) pair and walks
+// tiles of 8 frames (4096 per-channel samples) of that song:
+//
+//   1. TMA: every thread issues one 1-D bulk copy (cp.async.bulk, SASS UBLKCP) of its 32-sample row
+//      into a padded shared-memory row (row stride = row bytes + 16, so that the 128-bit reads of the
+//      next step are bank-conflict free); completion is tracked by one mbarrier per CTA. The copy for
+//      the next tile is issued as soon as the rows are consumed, so it overlaps the FFTs.
+//   2. Per row: front-end (F32 input: 23-tap half-band 2:1 decimation + int16 quantisation, bit-exact
+//      with blx_frontend.h) or stereo down-mix (S16 input: (L + R) / 2, C truncation, reference
+//      src/frequency_sort.c:71-74), times the Hann window (reference src/frequency_sort.c:40-42,74),
+//      written to the FFT staging buffer. In FULL mode the same registers feed
+//        - the exact integer histogram of sample values -1904..+1902 (the only bins that can reach the
+//          integral of reference src/amplitude_sort.c:69-71 after 301 smoothing passes),
+//        - sum / sum of squares / first and last non-zero index (reference src/helpers.c:30-49,
+//          src/amplitude_sort.c:26-31),
+//        - for F32 input, the decimated int16 stream consumed by the envelope pass.
+//   3. Eight 512-point real FFTs at once, 16 threads each (fft16.cuh), and per-bin |X_d|^2 accumulated
+//      in registers over all tiles of the CTA (reference src/frequency_sort.c:83-93).
+//
+// At the end the eight per-group accumulators are reduced in a fixed order into one partial spectrum
+// per CTA; the epilogue kernel (epilogue.cu) sums the partials of a song in order, so results are
+// deterministic run to run.
+#include "blx_common.cuh"
+#include "fft16.cuh"
+#include "kernels.h"
+
+namespace blx {
+
+namespace {
+
+constexpr int kP1Threads = 128;
+constexpr int kP1FramesPerTile = 8;
+constexpr int kP1TileM = kP1FramesPerTile * kWin; // 4096 per-channel samples per tile
+constexpr int kFinFrame = 16 * 36;                // floats per staged frame: 16 chunks of 32 (+4 pad)
+
+template <int KIND> struct RowGeom;
+template <> struct RowGeom<kInF32> { static constexpr int elems = 64, ebytes = 4, halo = 1; };
+template <> struct RowGeom<kInS16Stereo> { static constexpr int elems = 64, ebytes = 2, halo = 0; };
+template <> struct RowGeom<kInS16Mono> { static constexpr int elems = 32, ebytes = 2, halo = 0; };
+
+template <int KIND> struct P1Smem {
+    using G = RowGeom<KIND>;
+    static constexpr int row_bytes = G::elems * G::ebytes;
+    static constexpr int row_stride = row_bytes + 16;
+    static constexpr int n_slots = kP1Threads + 2 * G::halo;
+    static constexpr int raw_bytes = n_slots * row_stride;
+    static constexpr int off_raw = 0;
+    static constexpr int off_fin = (raw_bytes + 127) / 128 * 128;
+    static constexpr int fin_bytes = kP1FramesPerTile * kFinFrame * 4; // 18432; also 8 KB reduction scratch
+    static constexpr int off_hann = off_fin + fin_bytes;
+    static constexpr int off_tw1 = off_hann + kFinFrame * 4;
+    static constexpr int off_tw2 = off_tw1 + 256 * 8;
+    static constexpr int off_bar = off_tw2 + 128 * 8;
+    static constexpr int off_hist = off_bar + 16;
+    static constexpr int bytes_lite = off_hist;
+    static constexpr int bytes_full = off_hist + kHistStride * 4;
+};
+
+struct RunHist { // run-length compaction in front of the shared-memory histogram atomics
+    int val;
+    unsigned cnt;
+};
+__device__ __forceinline__ void rh_flush(RunHist &rh, unsigned *hist) {
+    const unsigned bin = (unsigned)(rh.val + 32768 - kHistLo);
+    if (rh.cnt && bin < (unsigned)kHistBins) atomicAdd(&hist[bin], rh.cnt);
+}
+__device__ __forceinline__ void rh_push(RunHist &rh, unsigned *hist, int v, unsigned c) {
+    if (v == rh.val) {
+        rh.cnt += c;
+    } else {
+        rh_flush(rh, hist);
+        rh.val = v;
+        rh.cnt = c;
+    }
+}
+
+struct ThreadStats {
+    long long sum;
+    unsigned long long sumsq;
+    int first_nz, last_nz;
+};
+
+} // namespace
+
+template <int KIND, bool FULL>
+__global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
+    using SM = P1Smem<KIND>;
+    using G = RowGeom<KIND>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SongDesc sd = p.songs[blockIdx.y];
+    const int part = blockIdx.x;
+    if (part >= sd.n_parts) return;
+
+    unsigned char *raw = smem + SM::off_raw;
+    float *fin = reinterpret_cast<float *>(smem + SM::off_fin);
+    float *hannp = reinterpret_cast<float *>(smem + SM::off_hann);
+    float2 *tw1 = reinterpret_cast<float2 *>(smem + SM::off_tw1);
+    float2 *tw2 = reinterpret_cast<float2 *>(smem + SM::off_tw2);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::off_bar);
+    unsigned *hist = reinterpret_cast<unsigned *>(smem + SM::off_hist);
+
+    const int tid = threadIdx.x;
+    const int lane16 = tid & 15;
+    const int grp = tid >> 4; // frame slot inside the tile == FFT group
+    const unsigned hw_mask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+
+    // ---- one-time setup: tables into shared memory, histogram cleared, barrier armed
+    for (int i = tid; i < kWin; i += kP1Threads) hannp[(i >> 5) * 36 + (i & 31)] = p.hann[i];
+    for (int i = tid; i < 256; i += kP1Threads) tw1[i] = p.tw1[i];
+    for (int i = tid; i < 128; i += kP1Threads) tw2[i] = p.tw2[i];
+    if (FULL)
+        for (int i = tid; i < kHistStride; i += kP1Threads) hist[i] = 0u;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(p.pcm) + (size_t)sd.pcm_off * G::ebytes;
+    const long long n_elems = sd.n_elems;
+
+    // Issues the bulk copies of one tile. Row `row` (may be -1 or 128 for the halo) starts at input
+    // element tile * 128 * elems + row * elems; it is copied in full iff it starts inside the song
+    // (the buffer is readable up to the next multiple of BLX_ALIGN_ELEMS).
+    auto issue_tile = [&](int tile) {
+        const long long e0 = (long long)tile * kP1Threads * G::elems;
+        fence_proxy_async();
+        if (tid == 0) {
+            long long first = e0 - (long long)G::halo * G::elems;
+            if (first < 0) first = 0;
+            long long last = e0 + (long long)(kP1Threads + G::halo) * G::elems; // exclusive
+            const long long lim = (n_elems + G::elems - 1) / G::elems * G::elems;
+            if (last > lim) last = lim;
+            const long long rows = (last > first) ? (last - first) / G::elems : 0;
+            mbar_arrive_expect_tx(bar, (unsigned)(rows * SM::row_bytes));
+        }
+        {
+            const long long es = e0 + (long long)tid * G::elems;
+            if (es < n_elems)
+                tma_load_1d(raw + (size_t)(tid + G::halo) * SM::row_stride, src + es * G::ebytes, SM::row_bytes, bar);
+        }
+        if (G::halo && tid < 2) {
+            const long long es = (tid == 0) ? e0 - G::elems : e0 + (long long)kP1Threads * G::elems;
+            const int slot = (tid == 0) ? 0 : kP1Threads + 1;
+            if (es >= 0 && es < n_elems)
+                tma_load_1d(raw + (size_t)slot * SM::row_stride, src + es * G::ebytes, SM::row_bytes, bar);
+        }
+    };
+
+    float accA[8], accB[8], acc128 = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) accA[d] = accB[d] = 0.0f;
+
+    ThreadStats ts;
+    ts.sum = 0; ts.sumsq = 0ull; ts.first_nz = 0x7fffffff; ts.last_nz = -1;
+    RunHist rh;
+    rh.val = 0x40000000; rh.cnt = 0;
+
+    unsigned parity = 0;
+    int tile = part;
+    if (tile < sd.n_tiles) issue_tile(tile);
+
+    for (; tile < sd.n_tiles; tile += sd.n_parts) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        const long long e0 = (long long)tile * kP1Threads * G::elems;
+        // ---- boundary fix-up (block-uniform): rows that were not copied, and the part of the last
+        // row beyond the song, must read as zero (x[i] = 0 outside [0, n_in), blx_frontend.h).
+        const bool edge = (e0 - (long long)G::halo * G::elems < 0) ||
+                          (e0 + (long long)(kP1Threads + G::halo) * G::elems > n_elems);
+        if (edge) {
+            for (int slot = tid; slot < SM::n_slots; slot += kP1Threads) {
+                const long long es = e0 + (long long)(slot - G::halo) * G::elems;
+                unsigned char *row = raw + (size_t)slot * SM::row_stride;
+                if (es < 0 || es >= n_elems) {
+                    for (int i = 0; i < SM::row_bytes / 16; ++i) reinterpret_cast<int4 *>(row)[i] = make_int4(0, 0, 0, 0);
+                } else if (es + G::elems > n_elems) {
+                    const int keep = (int)(n_elems - es);
+                    if (G::ebytes == 4) {
+                        for (int i = keep; i < G::elems; ++i) reinterpret_cast<float *>(row)[i] = 0.0f;
+                    } else {
+                        for (int i = keep; i < G::elems; ++i) reinterpret_cast<short *>(row)[i] = 0;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- per-row front-end / down-mix + window -> fin, plus FULL-mode side products
+        const long long m0 = (long long)tile * kP1TileM + tid * 32; // first per-channel sample of this row
+        float *fout = fin + grp * kFinFrame + lane16 * 36;
+        const float *hrow = hannp + lane16 * 36;
+
+        if (KIND == kInF32) {
+            const float H[BLX_FE_NPAIRS] = BLX_FE_TAPS;
+            const float4 *rowp = reinterpret_cast<const float4 *>(raw + (size_t)(tid + 1) * SM::row_stride);
+            const float4 *prevp = reinterpret_cast<const float4 *>(raw + (size_t)tid * SM::row_stride);
+            const float4 *nextp = reinterpret_cast<const float4 *>(raw + (size_t)(tid + 2) * SM::row_stride);
+            const long long n_out = n_elems >> 1;
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float4 a = prevp[13 + i], b = rowp[i];
+                w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
+                w[12 + 4 * i] = b.x; w[12 + 4 * i + 1] = b.y; w[12 + 4 * i + 2] = b.z; w[12 + 4 * i + 3] = b.w;
+            }
+            short qv[32];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int q4 = 2 * s + 3 + h2;
+                    const float4 a = (q4 < 16) ? rowp[q4] : nextp[q4 - 16];
+                    w[24 + 4 * h2] = a.x; w[25 + 4 * h2] = a.y; w[26 + 4 * h2] = a.z; w[27 + 4 * h2] = a.w;
+                }
+                float o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = 12 + 2 * u;
+                    float acc = __fmul_rn(BLX_FE_CENTER, w[c]);
+#pragma unroll
+                    for (int k = 0; k < BLX_FE_NPAIRS; ++k)
+                        acc = __fmaf_rn(H[k], __fadd_rn(w[c - (2 * k + 1)], w[c + (2 * k + 1)]), acc);
+                    float q = rintf(acc);
+                    q = fminf(fmaxf(q, -32768.0f), 32767.0f);
+                    o[u] = q;
+                    if (FULL) {
+                        const int qi = (int)q;
+                        qv[4 * s + u] = (short)qi;
+                        const long long t = m0 + 4 * s + u;
+                        if (t < n_out) {
+                            ts.sum += 2 * qi;
+                            ts.sumsq += 2ull * (unsigned long long)(qi * qi);
+                            if (qi != 0) {
+                                const int i0 = (int)(2 * t);
+                                ts.first_nz = min(ts.first_nz, i0);
+                                ts.last_nz = max(ts.last_nz, i0 + 1);
+                            }
+                            rh_push(rh, hist, qi, 2u);
+                        }
+                    }
+                }
+                const float4 hv = *reinterpret_cast<const float4 *>(hrow + 4 * s);
+                float4 r4;
+                r4.x = o[0] * hv.x; r4.y = o[1] * hv.y; r4.z = o[2] * hv.z; r4.w = o[3] * hv.w;
+                *reinterpret_cast<float4 *>(fout + 4 * s) = r4;
+#pragma unroll
+                for (int i = 0; i < 24; ++i) w[i] = w[i + 8];
+            }
+            if (FULL && m0 < n_out) { // decimated stream for the envelope pass (mono: L == R)
+                int4 *dst = reinterpret_cast<int4 *>(p.qout + sd.q_off + m0);
+                const int4 *srcq = reinterpret_cast<const int4 *>(qv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = srcq[i]; // q rows are padded to 32 samples by the engine
+            }
+        } else {
+            const int4 *rowp = reinterpret_cast<const int4 *>(raw + (size_t)tid * SM::row_stride);
+            constexpr int per_vec = (KIND == kInS16Stereo) ? 4 : 8; // per-channel samples per 16-byte load
+            const long long i0 = (long long)tile * kP1Threads * G::elems + (long long)tid * G::elems;
+#pragma unroll
+            for (int vix = 0; vix < SM::row_bytes / 16; ++vix) {
+                const int4 raw4 = rowp[vix];
+                const int wds[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+                float o[per_vec];
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    const int lo = (int)(short)(wds[wi] & 0xffff);
+                    const int hi = wds[wi] >> 16;
+                    if (KIND == kInS16Stereo) o[wi] = (float)((lo + hi) / 2); // C truncation toward zero
+                    else { o[2 * wi] = (float)lo; o[2 * wi + 1] = (float)hi; }
+                    if (FULL) {
+                        const long long ii = i0 + vix * 8 + wi * 2;
+                        const int sv[2] = {lo, hi};
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            if (ii + e < n_elems) {
+                                ts.sum += sv[e];
+                                ts.sumsq += (unsigned long long)(sv[e] * sv[e]);
+                                if (sv[e] != 0) {
+                                    ts.first_nz = min(ts.first_nz, (int)(ii + e));
+                                    ts.last_nz = max(ts.last_nz, (int)(ii + e));
+                                }
+                                rh_push(rh, hist, sv[e], 1u);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < per_vec / 4; ++q4) {
+                    const int j = vix * per_vec + q4 * 4;
+                    const float4 hv = *reinterpret_cast<const float4 *>(hrow + j);
+                    float4 r4;
+                    r4.x = o[q4 * 4] * hv.x; r4.y = o[q4 * 4 + 1] * hv.y;
+                    r4.z = o[q4 * 4 + 2] * hv.z; r4.w = o[q4 * 4 + 3] * hv.w;
+                    *reinterpret_cast<float4 *>(fout + j) = r4;
+                }
+            }
+        }
+        __syncthreads(); // rows consumed, fin complete
+
+        // ---- prefetch the next tile of this CTA while the FFTs run
+        if (tile + sd.n_parts < sd.n_tiles) issue_tile(tile + sd.n_parts);
+
+        // ---- 8 x (512-point real FFT + power accumulation), 16 threads per frame
+        if (tile * kP1FramesPerTile + grp < sd.n_frames) {
+            float2 *xchg = reinterpret_cast<float2 *>(fin + grp * kFinFrame);
+            float2 v[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) v[a] = *reinterpret_cast<const float2 *>(fin + grp * kFinFrame + 36 * a + 2 * lane16);
+            __syncwarp(hw_mask);
+            fft256_halfwarp<float>(v, lane16, xchg, tw1, hw_mask);
+            __syncwarp(hw_mask);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) xchg[lane16 + 16 * fft16_out_index(r)] = v[r];
+            __syncwarp(hw_mask);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const int k = lane16 + 16 * d;
+                if (k != 0) { // bins k and 512/2 - k from Z[k], Z[256 - k]
+                    const float2 A = v[fft16_reg_of(d)];
+                    const float2 B = xchg[256 - k];
+                    const float2 wk = tw2[k];
+                    const float sr = A.x + B.x, si = A.y - B.y;
+                    const float dr = A.x - B.x, di = A.y + B.y;
+                    const float tr = dr * wk.x - di * wk.y;
+                    const float ti = dr * wk.y + di * wk.x;
+                    const float ar = sr + ti, ai = si - tr;
+                    const float br = sr - ti, bi = si + tr;
+                    accA[d] += 0.25f * (ar * ar + ai * ai);
+                    accB[d] += 0.25f * (br * br + bi * bi);
+                }
+            }
+            if (lane16 == 0) {
+                const float2 A = v[fft16_reg_of(8)]; // Z[128] -> X[128] = conj(Z[128])
+                acc128 += A.x * A.x + A.y * A.y;
+            }
+        }
+        __syncthreads(); // fin / xchg free for the next tile
+    }
+
+    // ---- CTA partial spectrum: fixed-order reduction over the 8 groups
+    float *red = fin; // [8][256]
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        const int k = lane16 + 16 * d;
+        red[grp * 256 + k] = accA[d];
+        if (k != 0) red[grp * 256 + 256 - k] = accB[d];
+    }
+    if (lane16 == 0) red[grp * 256 + 128] = acc128;
+    __syncthreads();
+    for (int k = tid; k < 256; k += kP1Threads) {
+        float s = 0.0f;
+#pragma unroll
+        for (int g2 = 0; g2 < kP1FramesPerTile; ++g2) s += red[g2 * 256 + k];
+        p.partials[(size_t)(sd.part_off + part) * 256 + k] = (k == 0) ? 0.0f : s;
+    }
+
+    if (FULL) {
+        rh_flush(rh, hist);
+        // statistics: warp shuffle reduction, then one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ts.sum += __shfl_xor_sync(0xffffffffu, ts.sum, o);
+            ts.sumsq += __shfl_xor_sync(0xffffffffu, ts.sumsq, o);
+            ts.first_nz = min(ts.first_nz, __shfl_xor_sync(0xffffffffu, ts.first_nz, o));
+            ts.last_nz = max(ts.last_nz, __shfl_xor_sync(0xffffffffu, ts.last_nz, o));
+        }
+        SongStats *st = p.stats + blockIdx.y;
+        if ((tid & 31) == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(&st->sum), (unsigned long long)ts.sum);
+            atomicAdd(&st->sumsq, ts.sumsq);
+            if (ts.last_nz >= 0) {
+                atomicMax(&st->first_inv, 0x7fffffffu - (unsigned)ts.first_nz);
+                atomicMax(&st->last_p1, (unsigned)ts.last_nz + 1u);
+            }
+        }
+        __syncthreads();
+        unsigned *ghist = p.hist + (size_t)blockIdx.y * kHistStride;
+        for (int i = tid; i < kHistBins; i += kP1Threads) {
+            const unsigned c = hist[i];
+            if (c) atomicAdd(&ghist[i], c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- launcher
+template <int KIND, bool FULL> static cudaError_t launch_one(const Pass1Params &p, int max_parts, int n_songs, cudaStream_t st) {
+    using SM = P1Smem<KIND>;
+    const int bytes = FULL ? SM::bytes_full : SM::bytes_lite;
+    static bool configured = false;
+    if (!configured) { // one process drives one device (one rank per GPU)
+        cudaError_t e = cudaFuncSetAttribute(pass1_kernel<KIND, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((unsigned)max_parts, (unsigned)n_songs);
+    pass1_kernel<KIND, FULL><<<grid, kP1Threads, bytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pass1(int kind, bool full, const Pass1Params &p, int max_parts, int n_songs, cudaStream_t st) {
+    switch (kind) {
+        case kInF32: return full ? launch_one<kInF32, true>(p, max_parts, n_songs, st) : launch_one<kInF32, false>(p, max_parts, n_songs, st);
+        case kInS16Stereo: return full ? launch_one<kInS16Stereo, true>(p, max_parts, n_songs, st) : launch_one<kInS16Stereo, false>(p, max_parts, n_songs, st);
+        case kInS16Mono: return full ? launch_one<kInS16Mono, true>(p, max_parts, n_songs, st) : launch_one<kInS16Mono, false>(p, max_parts, n_songs, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+int pass1_tile_msamples() { return kP1TileM; }
+
+} // namespace blx

@@ -1,0 +1,179 @@
+"""Python face of the device C-ABI (include/blx.h): one Engine per GPU / process.
+
+Host-buffer calls take numpy arrays; device-resident calls take raw device pointers
+(e.g. torch.Tensor.data_ptr()) — PyTorch is only the allocator / stream / collective plumbing.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+
+DO_AMPLITUDE, DO_FREQUENCY, DO_ENVELOPE, DO_ALL = 0x1, 0x2, 0x4, 0x7
+FMT_S16, FMT_F32 = 0, 1
+ALIGN_ELEMS = 64
+K_PASS1, K_EPILOGUE, K_ENVELOPE, K_TAIL, K_DISTANCE, K_COUNT = 0, 1, 2, 3, 4, 5
+SONG_TOO_SHORT, SONG_SILENT, SONG_FLAT = 0x1, 0x2, 0x4
+
+RESULT_DTYPE = np.dtype([("tempo", "<f4"), ("amplitude", "<f4"), ("frequency", "<f4"), ("attack", "<f4"),
+                         ("force", "<f4"), ("calm_or_loud", "<i4"), ("beat", "<i4"), ("status", "<i4")])
+assert RESULT_DTYPE.itemsize == ctypes.sizeof(L.BlxResult) == 32
+
+
+class BlxError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, device=0, chunk_bytes=None):
+        self._lib = L.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.blx_init(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise BlxError(f"blx_init(device={device}) failed ({rc}): {self._lib.blx_last_error().decode()}")
+        self._h = h
+        self.device = int(device)
+        if chunk_bytes:
+            self._ck(self._lib.blx_configure(self._h, int(chunk_bytes)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.blx_shutdown(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise BlxError(f"blx call failed ({rc}): {self._lib.blx_last_error().decode()}")
+
+    # ------------------------------------------------------------------ host buffers
+    def analyze_s16(self, songs, durations, channels=None, what=DO_ALL):
+        """songs: list of int16 numpy arrays (interleaved). Returns a RESULT_DTYPE array."""
+        n = len(songs)
+        songs = [np.ascontiguousarray(s, dtype=np.int16) for s in songs]
+        ptrs = (ctypes.c_void_p * n)(*[s.ctypes.data for s in songs])
+        lens = (ctypes.c_int * n)(*[len(s) for s in songs])
+        durs = (ctypes.c_uint64 * n)(*[int(d) for d in durations])
+        chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        self._ck(self._lib.blx_analyze_batch_s16(self._h, ptrs, lens, chs, durs, n, what,
+                                                 out.ctypes.data_as(ctypes.POINTER(L.BlxResult))))
+        return out
+
+    def analyze_f32(self, songs, what=DO_ALL):
+        """songs: list of float32 numpy arrays (44.1 kHz mono)."""
+        n = len(songs)
+        songs = [np.ascontiguousarray(s, dtype=np.float32) for s in songs]
+        ptrs = (ctypes.c_void_p * n)(*[s.ctypes.data for s in songs])
+        lens = (ctypes.c_int64 * n)(*[len(s) for s in songs])
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        self._ck(self._lib.blx_analyze_batch_f32(self._h, ptrs, lens, n, what,
+                                                 out.ctypes.data_as(ctypes.POINTER(L.BlxResult))))
+        return out
+
+    def analyze_host_ptrs(self, fmt, ptrs, lens, durations=None, channels=None, what=DO_ALL, out=None):
+        """Like analyze_s16 / analyze_f32 on raw host addresses (e.g. pinned torch tensors)."""
+        n = len(ptrs)
+        cptrs = (ctypes.c_void_p * n)(*[int(p) for p in ptrs])
+        if out is None:
+            out = np.zeros(n, dtype=RESULT_DTYPE)
+        res = out.ctypes.data_as(ctypes.POINTER(L.BlxResult))
+        if fmt == FMT_F32:
+            clens = (ctypes.c_int64 * n)(*[int(x) for x in lens])
+            self._ck(self._lib.blx_analyze_batch_f32(self._h, cptrs, clens, n, what, res))
+        else:
+            clens = (ctypes.c_int * n)(*[int(x) for x in lens])
+            durs = (ctypes.c_uint64 * n)(*[int(d) for d in durations])
+            chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
+            self._ck(self._lib.blx_analyze_batch_s16(self._h, cptrs, clens, chs, durs, n, what, res))
+        return out
+
+    # ------------------------------------------------------------------ device resident
+    def analyze_device(self, fmt, d_pcm, offsets, lengths, d_out, durations=None, channels=None, what=DO_ALL,
+                       stream=None):
+        n = len(offsets)
+        offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+        lens = (ctypes.c_int64 * n)(*[int(x) for x in lengths])
+        durs = (ctypes.c_uint64 * n)(*[int(d) for d in durations]) if durations is not None else None
+        chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
+        self._ck(self._lib.blx_analyze_device(self._h, fmt, ctypes.c_void_p(int(d_pcm)), offs, lens, chs, durs, n,
+                                              what, ctypes.c_void_p(int(d_out)),
+                                              ctypes.c_void_p(int(stream)) if stream else None))
+
+    def spectral_device(self, fmt, d_pcm, offsets, lengths, d_frequency, channels=None, stream=None):
+        n = len(offsets)
+        offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+        lens = (ctypes.c_int64 * n)(*[int(x) for x in lengths])
+        chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
+        self._ck(self._lib.blx_spectral_device(self._h, fmt, ctypes.c_void_p(int(d_pcm)), offs, lens, chs, n,
+                                               ctypes.c_void_p(int(d_frequency)),
+                                               ctypes.c_void_p(int(stream)) if stream else None))
+
+    # ------------------------------------------------------------------ distances
+    def distance_matrix(self, vectors, cosine=False):
+        v = np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, 4)
+        out = np.zeros((len(v), len(v)), dtype=np.float32)
+        f = self._lib.blx_cosine_matrix if cosine else self._lib.blx_distance_matrix
+        self._ck(f(self._h, v.ctypes.data_as(L.c_f32p), len(v), out.ctypes.data_as(L.c_f32p)))
+        return out
+
+    def distance_rows_device(self, d_vectors, n, row0, n_rows, d_out, cosine=False, stream=None):
+        self._ck(self._lib.blx_distance_rows_device(self._h, ctypes.c_void_p(int(d_vectors)), n, row0, n_rows,
+                                                    1 if cosine else 0, ctypes.c_void_p(int(d_out)),
+                                                    ctypes.c_void_p(int(stream)) if stream else None))
+
+    def distance_nearest_device(self, d_vectors, n, row0, n_rows, d_index, d_dist, d_sum, stream=None):
+        self._ck(self._lib.blx_distance_nearest_device(
+            self._h, ctypes.c_void_p(int(d_vectors)), n, row0, n_rows,
+            ctypes.c_void_p(int(d_index)) if d_index else None, ctypes.c_void_p(int(d_dist)) if d_dist else None,
+            ctypes.c_void_p(int(d_sum)) if d_sum else None, ctypes.c_void_p(int(stream)) if stream else None))
+
+    # ------------------------------------------------------------------ helpers
+    def mean_variance(self, pcm, mean_in=None):
+        a = np.ascontiguousarray(pcm, dtype=np.int16)
+        m, v = ctypes.c_int(0), ctypes.c_int(0)
+        mi = ctypes.byref(ctypes.c_int(int(mean_in))) if mean_in is not None else None
+        self._ck(self._lib.blx_mean_variance_s16(self._h, a.ctypes.data_as(L.c_i16p), len(a), mi,
+                                                 ctypes.byref(m), ctypes.byref(v)))
+        return m.value, v.value
+
+    def rectangular_filter(self, out, inp, width=19):
+        out = np.array(out, dtype=np.float64, copy=True)
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        self._ck(self._lib.blx_rectangular_filter(self._h, out.ctypes.data_as(L.c_f64p), inp.ctypes.data_as(L.c_f64p),
+                                                  len(inp), width))
+        return out
+
+    def frontend_f32(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros(2 * (len(x) // 2), dtype=np.int16)
+        self._ck(self._lib.blx_frontend_f32(self._h, x.ctypes.data_as(L.c_f32p), len(x), out.ctypes.data_as(L.c_i16p)))
+        return out
+
+    def envelope_energy(self, pcm):
+        a = np.ascontiguousarray(pcm, dtype=np.int16)
+        nb = 2 * (len(a) // 512)
+        E = np.zeros(max(nb, 1), dtype=np.float64)
+        self._ck(self._lib.blx_envelope_energy_s16(self._h, a.ctypes.data_as(L.c_i16p), len(a), E.ctypes.data_as(L.c_f64p)))
+        return E[:nb]
+
+    # ------------------------------------------------------------------ measurement
+    def profile(self, on=True):
+        self._ck(self._lib.blx_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(self._lib.blx_profile_reset(self._h))
+
+    def profile_read(self):
+        ms = (ctypes.c_float * K_COUNT)()
+        n = (ctypes.c_int * K_COUNT)()
+        self._ck(self._lib.blx_profile_read(self._h, ms, n))
+        return {self._lib.blx_kernel_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(K_COUNT)}
+
+    def launch_count(self):
+        return int(self._lib.blx_launch_count(self._h))

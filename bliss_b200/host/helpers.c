@@ -1,0 +1,89 @@
+/* Lifecycle helpers and small numeric helpers of bliss.h.
+ *
+ * bl_free_song / bl_initialize_song / bl_version mirror reference src/helpers.c:3-28 (same
+ * ownership contract: the seven pointers come from the C heap and are NULLed after free).
+ * bl_mean / bl_variance (reference src/helpers.c:30-49) and bl_rectangular_filter (reference
+ * src/tempo_atk_sort.c:19-40) run on the GPU through blx.h like the analysers that use them.
+ */
+#include <pthread.h>
+
+#include "../../include/bliss.h"
+#include "engine_singleton.h"
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static blx_engine *g_engine = NULL;
+static int g_failed = 0;
+
+blx_engine *bl_engine_acquire(void) {
+    pthread_mutex_lock(&g_lock);
+    if (!g_engine && !g_failed) {
+        const char *dev = getenv("BLISS_DEVICE");
+        int rc = blx_init(dev ? atoi(dev) : 0, &g_engine);
+        if (rc != BLX_OK) {
+            fprintf(stderr, "bliss: cannot start the GPU engine: %s\n", blx_last_error());
+            g_engine = NULL;
+            g_failed = 1;
+        }
+    }
+    if (!g_engine) {
+        pthread_mutex_unlock(&g_lock);
+        return NULL;
+    }
+    return g_engine;
+}
+
+void bl_engine_release(void) { pthread_mutex_unlock(&g_lock); }
+
+void bl_free_song(struct bl_song *const song) {
+    free(song->artist);
+    free(song->title);
+    free(song->album);
+    free(song->tracknumber);
+    free(song->genre);
+    free(song->filename);
+    free(song->sample_array);
+    bl_initialize_song(song);
+}
+
+void bl_initialize_song(struct bl_song *const song) {
+    song->sample_array = NULL;
+    song->filename = NULL;
+    song->artist = NULL;
+    song->title = NULL;
+    song->album = NULL;
+    song->tracknumber = NULL;
+    song->genre = NULL;
+}
+
+float bl_version(void) {
+    printf("Using bliss analyzer version %0.1f.\n", BL_VERSION);
+    return (float)BL_VERSION;
+}
+
+int bl_mean(int16_t *sample_array, int nSamples) {
+    int mean = 0;
+    blx_engine *e = bl_engine_acquire();
+    if (!e) return 0;
+    if (blx_mean_variance_s16(e, sample_array, nSamples, NULL, &mean, NULL) != BLX_OK)
+        fprintf(stderr, "bliss: bl_mean failed: %s\n", blx_last_error());
+    bl_engine_release();
+    return mean;
+}
+
+int bl_variance(int16_t *sample_array, int nSamples, int mean) {
+    int var = 0;
+    blx_engine *e = bl_engine_acquire();
+    if (!e) return 0;
+    if (blx_mean_variance_s16(e, sample_array, nSamples, &mean, NULL, &var) != BLX_OK)
+        fprintf(stderr, "bliss: bl_variance failed: %s\n", blx_last_error());
+    bl_engine_release();
+    return var;
+}
+
+void bl_rectangular_filter(double *sample_array_out, double *sample_array_in, int nSamples, int smooth_width) {
+    blx_engine *e = bl_engine_acquire();
+    if (!e) return;
+    if (blx_rectangular_filter(e, sample_array_out, sample_array_in, nSamples, smooth_width) != BLX_OK)
+        fprintf(stderr, "bliss: bl_rectangular_filter failed: %s\n", blx_last_error());
+    bl_engine_release();
+}

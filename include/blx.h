@@ -1,0 +1,163 @@
+/* blx.h — the thin device C-ABI of the B200-native bliss engine.
+ *
+ * extern "C", plain pointers and sizes, no CUDA / torch types. The 15 functions of
+ * bliss.h are host-C wrappers over these entry points (the C files under bliss_b200/host); batch
+ * users (bench.py, the Python package, a cgo/JNI/ctypes binding) call them directly.
+ * Each entry point names the reference interface it replaces.
+ *
+ * All analysis work runs in hand-written sm_100a CUDA kernels (bliss_b200/csrc).
+ * There is NO CPU implementation behind these calls: without a CUDA device
+ * blx_init fails with BLX_ERR_CUDA and every other call with BLX_ERR_ARG.
+ *
+ * Threading: an engine may be used from one thread at a time; create one engine per
+ * thread/stream for concurrency. blx_last_error() is thread-local.
+ */
+#ifndef BLX_H_
+#define BLX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLX_OK 0
+#define BLX_ERR_CUDA -1  /* CUDA runtime / device error (see blx_last_error) */
+#define BLX_ERR_ARG -2   /* invalid argument */
+#define BLX_ERR_NOMEM -3 /* host or device allocation failed */
+
+/* Which analysers to run (bit mask). */
+#define BLX_DO_AMPLITUDE 0x1u /* replaces bl_amplitude_sort, reference src/amplitude_sort.c:12-80 */
+#define BLX_DO_FREQUENCY 0x2u /* replaces bl_frequency_sort, reference src/frequency_sort.c:20-140 */
+#define BLX_DO_ENVELOPE 0x4u  /* replaces bl_envelope_sort,  reference src/tempo_atk_sort.c:42-296 */
+#define BLX_DO_ALL 0x7u       /* + rating of reference src/analyze.c:63-79 */
+
+/* Per-song status bits in blx_result.status (0 = analysed). The reference has no error
+ * channel for these inputs: it loops forever, divides by zero or reads out of bounds
+ * (SURVEY.md §7.3 H5); the engine flags them and returns NaN ratings instead. */
+#define BLX_SONG_TOO_SHORT 0x1 /* nSamples < 1536 (no complete envelope hop) or duration == 0 */
+#define BLX_SONG_SILENT 0x2    /* every sample is zero */
+#define BLX_SONG_FLAT 0x4      /* integer variance is zero */
+
+/* Result record, 32 bytes. The first 16 bytes are exactly struct force_vector_s
+ * (reference include/bliss.h:26-31). */
+typedef struct blx_result {
+    float tempo;
+    float amplitude;
+    float frequency;
+    float attack;
+    float force;      /* reference src/analyze.c:68-72 */
+    int calm_or_loud; /* BL_LOUD 0 / BL_CALM 1 / BL_UNKNOWN 2, reference src/analyze.c:73-79 */
+    int beat;         /* onset count behind `tempo` (reference src/tempo_atk_sort.c:277-280) */
+    int status;
+} blx_result;
+
+typedef struct blx_engine blx_engine;
+
+/* PCM sample formats accepted by the device entry point. */
+#define BLX_FMT_S16 0 /* int16, interleaved, 22 050 Hz: the analysers' native input */
+#define BLX_FMT_F32 1 /* float32 mono 44.1 kHz, converted by the front-end of blx_frontend.h */
+
+/* Every song of a packed device buffer must start at an element offset that is a
+ * multiple of BLX_ALIGN_ELEMS and the buffer must stay readable up to the next
+ * multiple of BLX_ALIGN_ELEMS past each song's end (contents there are ignored). */
+#define BLX_ALIGN_ELEMS 64
+
+/* ---- lifecycle ------------------------------------------------------------ */
+int blx_device_count(void);
+int blx_init(int device, blx_engine **out);
+void blx_shutdown(blx_engine *e);
+const char *blx_last_error(void);
+
+/* Optional tuning, before the first analyse call. chunk_bytes: size of each of the
+ * two device staging buffers used by the host-buffer entry points (default 1 GiB). */
+int blx_configure(blx_engine *e, size_t chunk_bytes);
+
+/* ---- per-song analysis, HOST buffers (the end-to-end path) -------------------
+ * Replaces the analysis part of bl_analyze (reference src/analyze.c:43-79) for a
+ * batch of songs already decoded in host memory. Copies are chunked and
+ * double-buffered against the kernels. `out` is a host array of n_songs records. */
+int blx_analyze_batch_s16(blx_engine *e, const int16_t *const *pcm, const int *n_samples,
+                          const int *channels /* NULL => 2 */, const uint64_t *duration_s, int n_songs,
+                          unsigned what, blx_result *out);
+
+/* Same for 44.1 kHz mono float32 songs (n_in = samples per song); duration is
+ * n_in / 44100 whole seconds, nSamples = 2 * (n_in / 2). */
+int blx_analyze_batch_f32(blx_engine *e, const float *const *pcm, const int64_t *n_in, int n_songs,
+                          unsigned what, blx_result *out);
+
+/* ---- per-song analysis, DEVICE-resident packed buffer -------------------------
+ * d_pcm: device pointer (BLX_FMT_S16: int16_t*, BLX_FMT_F32: float*). offsets/lengths
+ * are HOST arrays in elements; channels (S16 only, NULL => 2) and duration_s (S16 only;
+ * F32 derives it) are HOST arrays. d_out: DEVICE array of n_songs blx_result.
+ * stream: a cudaStream_t passed as void* (NULL = the engine's own stream). The call
+ * only enqueues work; it does not synchronise. */
+int blx_analyze_device(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets,
+                       const int64_t *lengths, const int *channels, const uint64_t *duration_s, int n_songs,
+                       unsigned what, blx_result *d_out, void *stream);
+
+/* The fused window + rFFT-512 + per-bin power + band-ratio kernel ALONE
+ * (BASELINE.json configs[1]); writes only `frequency` per song to d_frequency
+ * (device float[n_songs]). Same buffer contract as blx_analyze_device. */
+int blx_spectral_device(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets,
+                        const int64_t *lengths, const int *channels, int n_songs, float *d_frequency,
+                        void *stream);
+
+/* ---- distances ----------------------------------------------------------------
+ * All-pairs euclidean distance with the float semantics of bl_distance
+ * (reference src/analyze.c:96-100: float sub/mul/add left to right, no FMA, sqrt
+ * correctly rounded). vectors: n x 4 floats (tempo, amplitude, frequency, attack). */
+int blx_distance_matrix(blx_engine *e, const float *vectors, int n, float *out /* n x n, host */);
+int blx_cosine_matrix(blx_engine *e, const float *vectors, int n, float *out); /* reference src/analyze.c:135-142 */
+
+/* Device slab: rows [row0, row0 + n_rows) of the n x n matrix into d_out (n_rows x n).
+ * mode 0 = euclidean, 1 = cosine similarity. */
+int blx_distance_rows_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows, int mode,
+                             float *d_out, void *stream);
+
+/* Fused epilogue for matrices that cannot be materialised (1 M x 1 M): per row of the
+ * slab, the nearest other song and the sum of its distances (a checksum in double). */
+int blx_distance_nearest_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows,
+                                int *d_nearest_index, float *d_nearest_dist, double *d_row_sum, void *stream);
+
+/* ---- small reference helpers on the device --------------------------------------
+ * bl_mean / bl_variance (reference src/helpers.c:30-49) and bl_rectangular_filter
+ * (reference src/tempo_atk_sort.c:19-40), host buffers. */
+/* mean_in: NULL => variance around the array's own integer mean (what the reference's callers pass,
+ * reference src/tempo_atk_sort.c:101-103); otherwise around *mean_in. The device pass returns the
+ * exact integer sums; sum (s - m)^2 = sum s^2 - 2 m sum s + n m^2 is evaluated in 64-bit integers. */
+int blx_mean_variance_s16(blx_engine *e, const int16_t *pcm, int n_samples, const int *mean_in, int *mean,
+                          int *variance);
+int blx_rectangular_filter(blx_engine *e, double *out, const double *in, int n, int width);
+
+/* Front-end alone (blx_frontend.h): host float32 in, host int16 stereo out
+ * (2 * (n_in / 2) values). */
+int blx_frontend_f32(blx_engine *e, const float *pcm, int64_t n_in, int16_t *out);
+
+/* Envelope intermediates for kernel-level parity tests: hop energies E[m]
+ * (reference src/tempo_atk_sort.c:150), 2 * (n_samples / 512) doubles, host. */
+int blx_envelope_energy_s16(blx_engine *e, const int16_t *pcm, int n_samples, double *energy);
+
+/* ---- measurement ------------------------------------------------------------------
+ * With profiling on, every kernel launch is bracketed by CUDA events on its own stream.
+ * blx_profile_read synchronises and returns, per kernel id, the accumulated device time
+ * (ms) and launch count since the last blx_profile_reset. */
+#define BLX_K_PASS1 0    /* front-end + Hann + rFFT-512 + |X|^2 (+ histogram, stats) */
+#define BLX_K_EPILOGUE 1 /* band ratios, 301-pass histogram smoothing, mean/variance */
+#define BLX_K_ENVELOPE 2 /* normalise + FIR + FP64 rFFT-512 + float-accumulated energy */
+#define BLX_K_TAIL 3     /* IIR, diff, box filters, onset count, rating */
+#define BLX_K_DISTANCE 4
+#define BLX_K_COUNT 5
+int blx_profile_enable(blx_engine *e, int on);
+int blx_profile_reset(blx_engine *e);
+int blx_profile_read(blx_engine *e, float *ms /* [BLX_K_COUNT] */, int *launches /* [BLX_K_COUNT] */);
+const char *blx_kernel_name(int kernel_id);
+
+/* Total kernels launched by this engine since creation (bench.py's gpu_launches). */
+long long blx_launch_count(blx_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLX_H_ */

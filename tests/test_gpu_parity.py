@@ -1,0 +1,214 @@
+"""GPU: parity of the CUDA path against the oracle, through the C-ABI (include/blx.h) and the
+bliss.h wrappers. Tolerances (BASELINE.json north_star): every force_vector component within 1e-4
+relative of the reference, onset counts exact, distances bit-exact."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import bliss_b200
+from conftest import GOLDEN_DIR
+from synth import song_f32, song_s16
+from test_oracle import GOLDEN_S16
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4  # north_star: "every force_vector within 1e-4 relative of the reference"
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-30)
+
+
+def check_song(res, ref, tag=""):
+    assert res["status"] == 0, (tag, res)
+    assert int(res["beat"]) == ref["beat"], (tag, "beat", int(res["beat"]), ref["beat"])
+    for k in ("tempo", "amplitude", "frequency", "attack", "force"):
+        assert rel(float(res[k]), ref[k]) <= REL_TOL, (tag, k, float(res[k]), ref[k])
+    assert int(res["calm_or_loud"]) == ref["calm_or_loud"], tag
+
+
+# ---------------------------------------------------------------- config 1: the reference's own fixture
+def test_bl_analyze_golden_fixture(oracle):
+    L = bliss_b200.load()
+    s = bliss_b200.BlSong()
+    rc = L.bl_analyze(os.path.join(GOLDEN_DIR, "song.flac").encode(), ctypes.byref(s))
+    assert rc == 1  # BL_CALM
+    got = dict(force=s.force, tempo=s.force_vector.tempo, amplitude=s.force_vector.amplitude,
+               frequency=s.force_vector.frequency, attack=s.force_vector.attack)
+    # reference tests/test_analyze.c:30-35 with its own 1e-5 absolute tolerance (:5-11)
+    for k, v in got.items():
+        assert abs(v - GOLDEN_S16[k]) <= 1e-5, (k, v, GOLDEN_S16[k])
+    assert s.nSamples == 488138 and s.channels == 2 and s.duration == 11 and s.calm_or_loud == 1
+    # tempo = 4 * beat / duration - 30.4 with beat = 59 exactly
+    assert got["tempo"] == np.float32(np.float32(4 * np.float32(59) / np.float32(11)) - 30.4)
+    pcm = np.ctypeslib.as_array(ctypes.cast(s.sample_array, ctypes.POINTER(ctypes.c_int16)), (s.nSamples,)).copy()
+    # the three stand-alone analysers on the decoded song (reference include/bliss.h:184-217)
+    env = bliss_b200.EnvelopeResult()
+    L.bl_envelope_sort(ctypes.byref(s), ctypes.byref(env))
+    assert env.tempo == got["tempo"] and env.attack == got["attack"]
+    assert L.bl_amplitude_sort(ctypes.byref(s)) == got["amplitude"]
+    assert L.bl_frequency_sort(ctypes.byref(s)) == got["frequency"]
+    L.bl_free_song(ctypes.byref(s))
+    ref = oracle.analyze(pcm, 11)
+    assert got["amplitude"] == ref["amplitude"]  # histogram smoothing is replayed bit for bit
+    assert rel(got["frequency"], ref["frequency"]) <= 1e-5
+
+
+# ---------------------------------------------------------------- native int16 input
+S16_CASES = [(0, 6.0, False, 1.0), (1, 11.3, True, 0.4), (2, 3.0, True, 0.02), (3, 20.0, False, 1.6),
+             (4, 2.0, True, 0.9), (5, 33.0, False, 0.7)]
+
+
+def test_batch_s16_matches_oracle(engine, oracle):
+    songs = [song_s16(seed, sec, decorrelate=dec, gain=g) for seed, sec, dec, g in S16_CASES]
+    durs = [max(1, int(sec)) for _, sec, _, _ in S16_CASES]
+    res = engine.analyze_s16(songs, durs)
+    for i, pcm in enumerate(songs):
+        ref = oracle.analyze(pcm, durs[i])
+        check_song(res[i], ref, tag=f"s16 case {i}")
+        assert float(res[i]["amplitude"]) == ref["amplitude"], i  # bit-exact stage
+
+
+def test_ragged_batch_equals_single_song_calls(engine):
+    songs = [song_s16(20 + i, sec, decorrelate=bool(i & 1)) for i, sec in enumerate([2.0, 7.7, 3.3, 15.0, 2.5])]
+    durs = [2, 7, 3, 15, 2]
+    batch = engine.analyze_s16(songs, durs)
+    for i in range(len(songs)):
+        one = engine.analyze_s16([songs[i]], [durs[i]])
+        assert batch[i].tobytes() == one[0].tobytes(), i  # deterministic, independent of batching
+
+
+def test_small_chunks_equal_one_chunk(engine):
+    songs = [song_s16(40 + i, 2.0 + 0.7 * i) for i in range(6)]
+    durs = [2] * 6
+    a = engine.analyze_s16(songs, durs)
+    small = bliss_b200.Engine(0, chunk_bytes=1 << 20)  # forces one song per chunk, both slots in rotation
+    b = small.analyze_s16(songs, durs)
+    small.close()
+    assert a.tobytes() == b.tobytes()
+
+
+def test_mono_branch(engine, oracle):
+    pcm = song_s16(9, 5.0)[::2].copy()
+    res = engine.analyze_s16([pcm], [5], channels=[1], what=bliss_b200.DO_FREQUENCY)
+    assert rel(float(res[0]["frequency"]), oracle.frequency(pcm, channels=1)) <= 1e-5
+
+
+def test_envelope_intermediates(engine, oracle):
+    pcm = song_s16(7, 9.0, decorrelate=True, gain=0.5)
+    m, v = engine.mean_variance(pcm)
+    assert (m, v) == oracle.mean_variance(pcm)
+    assert engine.mean_variance(pcm, mean_in=m + 3)[1] == oracle.lib.orc_variance(
+        pcm.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), len(pcm), m + 3)
+    E = engine.envelope_energy(pcm)
+    Eo = oracle.envelope_energy(pcm)
+    assert E.shape == Eo.shape and np.all(E[-2:] == 0)
+    # E[m] is a float-rounded sum: equal to the oracle's up to rare single-ulp (6e-8) flips
+    assert np.max(np.abs(E - Eo) / np.maximum(Eo, 1e-300)) <= 2.4e-7
+    assert np.mean(E == Eo) > 0.99
+
+
+def test_rectangular_filter_helper(engine, oracle):
+    rng = np.random.default_rng(3)
+    x, out0 = rng.standard_normal(700), rng.standard_normal(700)
+    assert np.array_equal(engine.rectangular_filter(out0, x, 19), oracle.rectangular_filter(out0, x, 19))
+
+
+# ---------------------------------------------------------------- 44.1 kHz float32 input (front-end)
+def test_frontend_int16_stream_is_bit_exact(engine, oracle):
+    for seed, sec in [(0, 1.0), (1, 2.37), (2, 0.5)]:
+        x = song_f32(seed, sec)
+        if seed == 1:
+            x = (x * 3.9).astype(np.float32)  # drive into clipping
+        if seed == 2:
+            x = x[:-1]  # odd length
+        assert np.array_equal(engine.frontend_f32(x), oracle.frontend_f32(x)), seed
+
+
+def test_batch_f32_matches_oracle(engine, oracle):
+    secs = [4.0, 9.5, 30.0, 2.0]
+    songs = [song_f32(100 + i, s) for i, s in enumerate(secs)]
+    res = engine.analyze_f32(songs)
+    for i, x in enumerate(songs):
+        pcm = oracle.frontend_f32(x)  # identical int16 on both sides (blx_frontend.h)
+        ref = oracle.analyze(pcm, len(x) // 44100)
+        check_song(res[i], ref, tag=f"f32 case {i}")
+        assert float(res[i]["amplitude"]) == ref["amplitude"], i
+        # the fused path and the native-int16 path see the same samples
+        again = engine.analyze_s16([pcm], [len(x) // 44100])
+        assert again[0].tobytes() == res[i].tobytes(), i
+
+
+# ---------------------------------------------------------------- degenerate inputs
+def test_degenerate_inputs_are_flagged(engine):
+    silent = np.zeros(60000, dtype=np.int16)
+    short = song_s16(1, 0.05)
+    flat = np.full(60000, 7, dtype=np.int16)
+    ok = song_s16(2, 2.0)
+    res = engine.analyze_s16([silent, short, flat, ok], [1, 1, 1, 2])
+    assert res[0]["status"] & bliss_b200.engine.SONG_SILENT and np.isnan(res[0]["amplitude"])
+    assert res[1]["status"] & bliss_b200.engine.SONG_TOO_SHORT and np.isnan(res[1]["tempo"])
+    assert res[2]["status"] & bliss_b200.engine.SONG_FLAT
+    assert res[3]["status"] == 0
+    with pytest.raises(bliss_b200.BlxError):
+        engine.analyze_s16([ok], [2], channels=[3])
+
+
+# ---------------------------------------------------------------- distances
+def test_distance_matrix_bit_exact(engine, oracle):
+    rng = np.random.default_rng(11)
+    v = (rng.standard_normal((301, 4)) * np.array([10, 8, 12, 15])).astype(np.float32)
+    v[5] = v[17]  # a collision: distance exactly 0
+    d = engine.distance_matrix(v)
+    assert np.array_equal(d, oracle.distance_matrix(v))
+    assert d[5, 17] == 0 and np.array_equal(d, d.T) and np.all(np.diag(d) == 0)
+    c = engine.distance_matrix(v, cosine=True)
+    for i in range(0, 301, 13):
+        for j in range(0, 301, 7):
+            assert c[i, j] == np.float32(oracle.cosine_similarity(v[i], v[j])), (i, j)
+
+
+def test_distance_nearest_matches_matrix(engine):
+    import torch
+    rng = np.random.default_rng(12)
+    v = (rng.standard_normal((1000, 4)) * 10).astype(np.float32)
+    d = engine.distance_matrix(v).astype(np.float64)
+    dv = torch.from_numpy(v).cuda()
+    idx = torch.empty(1000, dtype=torch.int32, device="cuda")
+    dist = torch.empty(1000, dtype=torch.float32, device="cuda")
+    rsum = torch.empty(1000, dtype=torch.float64, device="cuda")
+    engine.distance_nearest_device(dv.data_ptr(), 1000, 0, 1000, idx.data_ptr(), dist.data_ptr(), rsum.data_ptr(),
+                                   stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    dm = d.copy()
+    np.fill_diagonal(dm, np.inf)
+    assert np.array_equal(idx.cpu().numpy(), dm.argmin(1))
+    assert np.array_equal(dist.cpu().numpy().astype(np.float64), dm.min(1))
+    assert np.allclose(rsum.cpu().numpy(), d.sum(1), rtol=1e-12)
+
+
+# ---------------------------------------------------------------- device-resident entry points
+def test_device_resident_batch_equals_host_batch(engine):
+    import torch
+    songs = [song_f32(200 + i, s) for i, s in enumerate([3.0, 5.2, 2.0])]
+    host = engine.analyze_f32(songs)
+    offs, total = [], 0
+    for x in songs:
+        offs.append(total)
+        total += (len(x) + 63) // 64 * 64 + 64
+    buf = torch.zeros(total, dtype=torch.float32, device="cuda")
+    for o, x in zip(offs, songs):
+        buf[o:o + len(x)] = torch.from_numpy(x).cuda()
+    out = torch.zeros(len(songs) * 8, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    engine.analyze_device(bliss_b200.FMT_F32, buf.data_ptr(), offs, [len(x) for x in songs], out.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    got = np.frombuffer(out.cpu().numpy().tobytes(), dtype=bliss_b200.RESULT_DTYPE)
+    assert got.tobytes() == host.tobytes()
+    # the spectral-only kernel (BASELINE.json configs[1]) gives the same frequency rating
+    freq = torch.zeros(len(songs), dtype=torch.float32, device="cuda")
+    engine.spectral_device(bliss_b200.FMT_F32, buf.data_ptr(), offs, [len(x) for x in songs], freq.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(freq.cpu().numpy(), host["frequency"])

@@ -1,0 +1,121 @@
+"""CPU: pins the oracle (our C restatement) against the reference's golden vectors and, bit for bit,
+against the reference's own analyser sources compiled verbatim (oracle/_ref)."""
+import ctypes
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+from synth import song_f32, song_s16
+
+# reference tests/test_analyze.c:30-45 (song.flac) — abs tolerance 1e-5 (tests/test_analyze.c:5-11)
+GOLDEN_S16 = dict(force=-20.777929, tempo=-8.945454, amplitude=-10.641844, frequency=-10.136086,
+                  attack=-15.560563, nSamples=488138, duration=11, beat=59)
+# reference tests/test_decode.c:16-17
+GOLDEN_S16_MD5 = "8a1bd824951c0433cc47fec5bf41d0a9"
+
+
+@pytest.fixture(scope="module")
+def song_pcm():
+    """PCM of the reference's audio/song.flac (copied to tests/golden), decoded by the product's host
+    FLAC reader — no GPU involved."""
+    import bliss_b200
+    L = bliss_b200.load()
+    s = bliss_b200.BlSong()
+    rc = L.bl_audio_decode(os.path.join(GOLDEN_DIR, "song.flac").encode(), ctypes.byref(s))
+    assert rc == 0
+    pcm = np.ctypeslib.as_array(ctypes.cast(s.sample_array, ctypes.POINTER(ctypes.c_int16)), (s.nSamples,)).copy()
+    meta = dict(nSamples=s.nSamples, channels=s.channels, sample_rate=s.sample_rate, duration=s.duration,
+                bitrate=s.bitrate, nb_bytes_per_sample=s.nb_bytes_per_sample, artist=s.artist, title=s.title,
+                album=s.album, tracknumber=s.tracknumber, genre=s.genre, resampled=s.resampled)
+    L.bl_free_song(ctypes.byref(s))
+    return pcm, meta
+
+
+def test_decode_matches_reference_pins(song_pcm):
+    pcm, meta = song_pcm
+    assert hashlib.md5(pcm.tobytes()).hexdigest() == GOLDEN_S16_MD5  # reference tests/test_decode.c:16-21
+    # reference tests/test_analyze.c:36-55
+    assert meta["nSamples"] == 488138 and meta["channels"] == 2 and meta["sample_rate"] == 22050
+    assert meta["bitrate"] == 233864 and meta["nb_bytes_per_sample"] == 2 and meta["duration"] == 11
+    assert (meta["artist"], meta["title"], meta["album"], meta["tracknumber"], meta["genre"]) == (
+        b"David TMX", b"Renaissance", b"Renaissance", b"02", b"Pop")
+
+
+def test_oracle_reproduces_golden_vector(oracle, song_pcm):
+    pcm, _ = song_pcm
+    r = oracle.analyze(pcm, GOLDEN_S16["duration"])
+    for k in ("force", "tempo", "amplitude", "frequency", "attack"):
+        assert abs(r[k] - GOLDEN_S16[k]) <= 1e-5, (k, r[k], GOLDEN_S16[k])
+    assert r["beat"] == GOLDEN_S16["beat"]
+    assert r["calm_or_loud"] == 1
+
+
+def test_reference_sources_reproduce_golden_vector(reflib, song_pcm):
+    pcm, _ = song_pcm
+    r = reflib.bl_analyze(pcm, GOLDEN_S16["duration"])
+    assert r["rc"] == 1
+    for k in ("force", "tempo", "amplitude", "frequency", "attack"):
+        assert abs(r[k] - GOLDEN_S16[k]) <= 1e-5, (k, r[k], GOLDEN_S16[k])
+
+
+def _bits(x):
+    return np.float32(x).tobytes()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_bit_identical_to_reference_sources(oracle, reflib, seed):
+    seconds = [3.0, 5.5, 8.0, 2.2, 12.0, 4.1][seed]
+    pcm = song_s16(seed, seconds, decorrelate=bool(seed % 2), gain=[1.0, 0.3, 0.05, 1.5, 0.8, 0.01][seed])
+    dur = max(1, int(seconds))
+    a = oracle.analyze(pcm, dur)
+    b = reflib.bl_analyze(pcm, dur)
+    for k in ("tempo", "amplitude", "frequency", "attack", "force"):
+        assert _bits(a[k]) == _bits(b[k]), (k, a[k], b[k])
+    assert a["calm_or_loud"] == b["calm_or_loud"]
+
+
+def test_oracle_mono_branch_matches_reference(oracle, reflib):
+    pcm = song_s16(11, 3.0)[::2].copy()  # reference src/frequency_sort.c:76-80
+    s, keep = reflib.make_song(pcm, 3, channels=1)
+    assert _bits(oracle.frequency(pcm, channels=1)) == _bits(reflib.lib.bl_frequency_sort(ctypes.byref(s)))
+
+
+def test_oracle_helpers_match_reference(oracle, reflib):
+    pcm = song_s16(3, 2.0, decorrelate=True)
+    m, v = oracle.mean_variance(pcm)
+    p = pcm.ctypes.data_as(ctypes.POINTER(ctypes.c_int16))
+    assert m == reflib.lib.bl_mean(p, len(pcm))
+    assert v == reflib.lib.bl_variance(p, len(pcm), m)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(500)
+    out0 = rng.standard_normal(500)
+    ours = oracle.rectangular_filter(out0, x, 19)
+    ref = out0.copy()
+    reflib.lib.bl_rectangular_filter(ref.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                     x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 500, 19)
+    assert np.array_equal(ours, ref)
+
+
+def test_oracle_distance_matches_reference(oracle, reflib):
+    rng = np.random.default_rng(7)
+    v = (rng.standard_normal((40, 4)) * 10).astype(np.float32)
+    for i in range(0, 40, 3):
+        for j in range(0, 40, 5):
+            assert _bits(oracle.distance(v[i], v[j])) == _bits(reflib.distance(v[i], v[j]))
+            if i != j:
+                assert _bits(oracle.cosine_similarity(v[i], v[j])) == _bits(reflib.cosine_similarity(v[i], v[j]))
+
+
+def test_frontend_spec_properties(oracle):
+    x = song_f32(1, 1.0)
+    q = oracle.frontend_f32(x)
+    assert len(q) == 2 * (len(x) // 2) and np.array_equal(q[0::2], q[1::2])
+    # DC gain = 32768 * 0.70710678 (blx_frontend.h)
+    dc = oracle.frontend_f32(np.full(4000, 0.25, dtype=np.float32))
+    assert abs(int(dc[2000]) - round(0.25 * 32768 * 0.70710678)) <= 1
+    # clipping
+    big = oracle.frontend_f32(np.full(4000, 4.0, dtype=np.float32))
+    assert big[2000] == 32767
