@@ -296,7 +296,14 @@ def run_ours(args):
     offs = [i * stride for i in range(B)]
     lens = [n_in] * B
     d_out = torch.zeros(B * 8, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # All timed work and the CUDA events that bracket it go to ONE explicit (non-default) stream: the
+    # C-ABI treats a NULL stream as "the engine's own", which torch events on the default stream
+    # would not see.
+    torch.cuda.synchronize()
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         eng.analyze_device(E.FMT_F32, buf.data_ptr(), offs, lens, d_out.data_ptr(), stream=stream)
@@ -417,6 +424,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     if out_host.tobytes() != res[:Be].tobytes():
+        for k in out_host.dtype.names:
+            d = np.flatnonzero(out_host[k] != res[:Be][k])
+            if len(d):
+                log(f"  field {k}: {len(d)} songs differ, e.g. song {d[0]}: host {out_host[k][d[0]]!r} device {res[k][d[0]]!r}")
         raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
     e2e = {"value": world * Be * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": world * Be * n_in * 4,
            "d2h_bytes_per_step": world * Be * 32, "songs_per_step": world * Be, "steps": e2e_steps,

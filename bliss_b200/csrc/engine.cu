@@ -277,9 +277,9 @@ struct ChunkPlan {
 static void plan_songs(int fmt, const long long *offsets, const long long *lengths, int channels_kind,
                        const unsigned long long *durations, int n, SongDesc *sd, ChunkPlan *plan) {
     const int tile_m = pass1_tile_msamples();
-    // enough CTAs for ~8 waves of 3 CTAs on 148 SMs, without splitting a song finer than one tile per CTA
-    const int target_ctas = 148 * 3 * 8;
-    const int parts_wanted = std::max(1, (target_ctas + n - 1) / n);
+    // A song is cut into parts of kTilesPerPart consecutive tiles, one CTA each. The cut depends on the
+    // song alone, so its partial spectra (and their float summation order) are the same in any batch.
+    const int kTilesPerPart = 16;
     plan->kind = (fmt == BLX_FMT_F32) ? kInF32 : channels_kind;
     long long env = 0, q = 0;
     int parts = 0;
@@ -309,7 +309,7 @@ static void plan_songs(int fmt, const long long *offsets, const long long *lengt
         d.n_hops = std::max(0, 2 * d.F - 2);
         d.env_off = env;
         env += round_up(std::max(2 * d.F, 2), 8);
-        d.n_parts = std::min(parts_wanted, d.n_tiles);
+        d.n_parts = (d.n_tiles + kTilesPerPart - 1) / kTilesPerPart;
         d.part_off = parts;
         parts += d.n_parts;
         plan->max_parts = std::max(plan->max_parts, d.n_parts);

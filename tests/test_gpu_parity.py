@@ -80,6 +80,16 @@ def test_ragged_batch_equals_single_song_calls(engine):
         assert batch[i].tobytes() == one[0].tobytes(), i  # deterministic, independent of batching
 
 
+def test_long_song_is_independent_of_batch_size(engine):
+    # the cut of a song into pass-1 parts (and so the float summation order of its spectrum) must
+    # depend on the song alone: alone, or as one of 48 songs, the record is byte-identical
+    long_song = song_s16(77, 45.0, decorrelate=True)
+    alone = engine.analyze_s16([long_song], [45])
+    fill = [song_s16(300 + i, 2.0) for i in range(47)]
+    batch = engine.analyze_s16(fill[:20] + [long_song] + fill[20:], [2] * 20 + [45] + [2] * 27)
+    assert batch[20].tobytes() == alone[0].tobytes()
+
+
 def test_small_chunks_equal_one_chunk(engine):
     songs = [song_s16(40 + i, 2.0 + 0.7 * i) for i in range(6)]
     durs = [2] * 6
