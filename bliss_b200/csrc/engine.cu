@@ -59,7 +59,7 @@ struct DevBuf {
 };
 
 struct Slot {
-    DevBuf pcm, songs, partials, hist, stats, norm, energy, q, results, freq;
+    DevBuf pcm, songs, partials, hist, stats, norm, energy, xlog, q, results, freq;
     SongDesc *h_songs = nullptr; // pinned
     size_t h_songs_cap = 0;
     blx_result *h_results = nullptr; // pinned
@@ -238,7 +238,7 @@ extern "C" void blx_shutdown(blx_engine *e) {
     for (int i = 0; i < 2; ++i) {
         Slot &s = e->slot[i];
         s.pcm.release(); s.songs.release(); s.partials.release(); s.hist.release(); s.stats.release();
-        s.norm.release(); s.energy.release(); s.q.release(); s.results.release(); s.freq.release();
+        s.norm.release(); s.energy.release(); s.xlog.release(); s.q.release(); s.results.release(); s.freq.release();
         if (s.h_songs) cudaFreeHost(s.h_songs);
         if (s.h_results) cudaFreeHost(s.h_results);
         if (s.copied) cudaEventDestroy(s.copied);
@@ -353,6 +353,7 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         CK(s.hist.reserve((size_t)n * kHistStride * sizeof(unsigned)));
         CK(s.stats.reserve((size_t)n * sizeof(SongStats)));
         CK(s.energy.reserve((size_t)std::max(plan.energy_total, 8ll) * sizeof(double)));
+        CK(s.xlog.reserve((size_t)std::max(plan.energy_total, 8ll) * sizeof(double)));
         if (plan.kind == kInF32) CK(s.q.reserve((size_t)std::max(plan.q_total, 64ll) * sizeof(short)));
     }
     CK(cudaMemcpyAsync(s.songs.p, s.h_songs, (size_t)n * sizeof(SongDesc), cudaMemcpyHostToDevice, st));
@@ -401,11 +402,15 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         ProfScope ps(e, BLX_K_ENVELOPE, st);
         CK(launch_envelope(p, plan.max_hops, n, st));
     }
+    if (what & BLX_DO_ENVELOPE) {
+        ProfScope ps(e, BLX_K_TAIL, st);
+        CK(launch_logcomp(static_cast<const double *>(s.energy.p), static_cast<double *>(s.xlog.p), plan.energy_total, st));
+    }
     {
         TailParams p;
         p.songs = d_songs;
         p.norm = static_cast<const SongNorm *>(s.norm.p);
-        p.energy = static_cast<const double *>(s.energy.p);
+        p.xlog = static_cast<const double *>(s.xlog.p);
         p.out = d_out;
         p.what = what;
         ProfScope ps(e, BLX_K_TAIL, st);

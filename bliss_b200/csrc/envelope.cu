@@ -11,23 +11,23 @@
 // FIR of the stream (same operands, same order), so a tile of 16 consecutive hops computes the
 // continuous FIR ONCE per sample (17 blocks of 256 samples) and only the first 16 outputs of each
 // window ("heads") separately with zero history. Then 16 FFTs run at once, 16 threads each
-// (fft16.cuh, double), and the even/odd split leaves |X_k|^2 of every hop in shared memory.
+// (fft16.cuh, double). A CTA walks kTilesPerCta tiles; the int16 tile of t+1 is fetched by one 1-D
+// bulk copy (cp.async.bulk / UBLKCP) as soon as the FIR of tile t has consumed the staging buffer.
 //
-// The float accumulation is a chain of 257 dependent roundings per hop: latency-, not
-// throughput-bound, and only 16 chains exist per tile. The CTA is therefore warp-specialised:
-//   warps 0..7  (producers)  TMA tile -> FIR -> heads -> 16 FFTs -> P[16][257]
-//   warp  8     (consumer)   lane h replays the chain of hop h of the PREVIOUS tile
-// so the chains of tile t overlap the FIR/FFT work of tile t+1 (named barriers 2/3 hand the P buffer
-// back and forth; the int16 tile of t+1 is fetched by one 1-D bulk copy, cp.async.bulk / UBLKCP, as
-// soon as the FIR of tile t has consumed the staging buffer). A CTA walks kTilesPerCta tiles.
-//
-// The chain itself: s <- (float)((double)s + p). While s stays inside one binade [2^e, 2^(e+1)) the
-// float grid is 2^(e-23), which is exactly the double grid of the binade [2^(e+29), 2^(e+30)). With
-// C = 2^(e+29) the value S' = s + C is exact and S' + p is ONE double addition whose IEEE rounding
-// (nearest, ties to even, same parity) is the rounding to the float grid; s + p >= 2^(e+1) shows as
-// bits(S' + p) >= bits(C + 2^(e+1)), and that step is redone through the reference's own
-// double-add / float-convert sequence and re-based. The result equals the reference's except when
-// s + p lies within 2^-53 (relative) of a float rounding midpoint (the reference rounds twice).
+// The float accumulation s <- (float)((double)s + p_k), k = 0..256, is a chain of 257 dependent
+// roundings (~50-75 cycles each on the FP64 + conversion pipes): run naively it idles the SM. It is
+// evaluated here by the 16 lanes that hold the hop's spectrum, as a SCAN:
+//   while s stays inside one binade [2^e, 2^(e+1)) its float grid is g = 2^(e-23) and
+//   RN_g(s + p) = s + RN_g(p) because s is a multiple of g; so with q = s / g (a 24-bit integer)
+//   the chain is q += I_k with I_k = RN_g(p_k) / g, which one double addition p_k + 1.5 * 2^52 * g
+//   leaves in the low mantissa word. Each lane converts its 16 bins, an integer prefix scan over the
+//   half-warp gives every partial sum at once, and the first bin k* at which q + prefix reaches 2^24
+//   (the sum leaves the binade) is found with a ballot. Bins below k* are final; bin k* is added with
+//   the reference's own double-add / float-convert sequence, which yields the next binade, and the
+//   scan restarts after k*. A hop needs one round per binade crossing (typically 2-6).
+// The result equals the reference's chain except when s + p_k lies within 2^-29 grid units of a
+// rounding midpoint (the reference rounds to double, then to float; exact ties follow the parity of
+// the magic constant instead of q).
 //
 // FP64 throughout; the summation order of the FIR is the reference's. FMA contraction is allowed
 // here (the reference has none): it perturbs E[m] by ~1e-16 relative, nine orders of magnitude
@@ -39,23 +39,21 @@
 namespace blx {
 
 namespace {
-constexpr int kEnvProducers = 256;               // 8 warps
-constexpr int kEnvThreads = kEnvProducers + 32;  // + 1 consumer warp
+constexpr int kEnvThreads = 256;                 // 8 warps = 16 half-warps = 16 FFTs
 constexpr int kEnvH = 16;                        // hops per tile
 constexpr int kTilesPerCta = 8;
 constexpr int kEnvSamples = (kEnvH + 1) * kHop;  // 4352 stream samples per tile
-constexpr int kPerThread = kEnvSamples / kEnvProducers; // 17 consecutive FIR outputs per thread
-static_assert(kPerThread * kEnvProducers == kEnvSamples, "tile must split evenly");
+constexpr int kPerThread = kEnvSamples / kEnvThreads; // 17 consecutive FIR outputs per thread
+static_assert(kPerThread * kEnvThreads == kEnvSamples, "tile must split evenly");
 constexpr int kXr = 17;                          // exchange row stride (doubles)
-constexpr int kXrElems = 16 * kXr;               // 272 doubles per transform (>= 257 for the split)
+constexpr int kXrElems = 16 * kXr;               // 272 doubles per transform
 
 constexpr int kOffQ = 0;                                   // short[4352]    TMA staging
 constexpr int kOffC = kOffQ + kEnvSamples * 2;             // double[4352]   continuous FIR output
 constexpr int kOffXhead = kOffC + kEnvSamples * 8;         // double[16][16] first 16 inputs of each window
 constexpr int kOffHeads = kOffXhead + 16 * 16 * 8;         // double[16][16] zero-history outputs
-constexpr int kOffXchg = kOffHeads + 16 * 16 * 8;          // double[16][272] one component at a time
-constexpr int kOffP = kOffXchg + kEnvH * kXrElems * 8;     // double[16][257] |X_k|^2 of the tile
-constexpr int kOffBar = kOffP + kEnvH * 257 * 8;
+constexpr int kOffXchg = kOffHeads + 16 * 16 * 8;          // double[16][272] exchange, one component at a time
+constexpr int kOffBar = kOffXchg + kEnvH * kXrElems * 8;
 constexpr int kEnvSmem = kOffBar + 16;
 static_assert(kEnvSmem <= 115712, "two CTAs per SM");
 
@@ -65,9 +63,6 @@ __device__ __forceinline__ double fir_tap(int k) {
                              0.0580037,  -0.0779167, 0.0882711, 0.9065095};
     return c[k];
 }
-
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // 256-point complex FFT across 16 lanes, exchanging one component at a time through xr
 // (16 x 17 doubles). In: v[a] = z[16 a + lane16]. Out: register r holds Z[lane16 + 16 * fft16_out_index(r)].
@@ -97,35 +92,64 @@ __device__ __forceinline__ void fft256_split(double2 (&v)[16], int lane16, doubl
     fft16<double>(v);
 }
 
-// State of one accumulation chain (see the header comment).
-struct Chain {
-    double Sp;   // s + C
-    double C;    // 2^(e+29), or 0 when s is zero / outside the normal float range (every step is redone)
-    long long L; // bits(C + 2^(e+1)): first value that leaves the binade
-    __device__ __forceinline__ void rebase(double r) { // r >= 0 holds a float value
-        const int ex = (__double2hiint(r) >> 20) & 0x7ff;
-        if (ex >= 1023 - 126 && ex <= 1023 + 127) {
-            const int chi = (ex + 29) << 20;
-            C = __hiloint2double(chi, 0);
-            Sp = r + C; // exact
-            L = ((long long)chi << 32) + (1ll << 24);
-        } else {
-            C = 0.0;
-            Sp = r;
-            L = 0;
+// sum_fft of reference src/tempo_atk_sort.c:142-150 for one hop, by the 16 lanes of a half-warp (see
+// the header comment). xr[k] = |X_k|^2, k = 0..256. Returns (double)sum_fft on every lane.
+__device__ __forceinline__ double float_chain_scan(const double *xr, int lane16, unsigned mask) {
+    const int lane_base = (threadIdx.x & 16); // first lane of this half-warp inside its warp
+    // bins 0..16 one by one (the sum climbs through several binades here), every lane redundantly
+    float sf = 0.0f;
+#pragma unroll
+    for (int k = 0; k <= 16; ++k) sf = (float)((double)sf + xr[k]);
+    double r = (double)sf;
+    int kdone = 16; // bins 0..kdone are in r
+    int row = 1;    // next row of 16 bins: 16 row + 1 .. 16 row + 16
+    while (row < 16) {
+        const int rhi = __double2hiint(r), rlo = __double2loint(r);
+        const int ex = (rhi >> 20) & 0x7ff;
+        if (ex < 1023 - 126 || ex > 1023 + 127) {
+            // zero, subnormal, inf or nan: no binade to scan in; one plain reference step
+            r = (double)(float)(r + xr[kdone + 1]);
+            kdone += 1;
+            if (kdone == 16 * row + 16) row += 1;
+            continue;
         }
-    }
-    __device__ __forceinline__ void add(double p) {
-        const double A = Sp + p;
-        if (__double_as_longlong(A) < L) {
-            Sp = A;
-        } else { // reference src/tempo_atk_sort.c:147 verbatim, then a new binade
-            const double s = Sp - C;
-            rebase((double)(float)(s + p));
+        // binade e = ex - 1023, float grid g = 2^(e-23); r = q g with 2^23 <= q < 2^24
+        const int hiM = ((ex + 29) << 20) | 0x80000; // M = 1.5 * 2^(e+29): ulp(M) = g
+        const double M = __hiloint2double(hiM, 0);
+        int q = ((rhi & 0xFFFFF) << 3) | (int)((unsigned)rlo >> 29) | 0x800000;
+        int kstar = 0, qb = 0;
+        for (; row < 16; ++row) {
+            const int k = 16 * row + 1 + lane16;
+            const double t = xr[k] + M; // low word = RN_g(p) / g while p < 2^32 g
+            unsigned I = (__double2hiint(t) == hiM) ? (unsigned)__double2loint(t) : (1u << 25);
+            I = min(I, 1u << 25);
+            if (k <= kdone) I = 0u;
+            int incl = (int)I;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const int up = __shfl_up_sync(mask, incl, o, 16);
+                if (lane16 >= o) incl += up;
+            }
+            const int tot = q + incl;
+            const unsigned crossed = (__ballot_sync(mask, tot >= (1 << 24)) >> lane_base) & 0xFFFFu;
+            if (crossed) {
+                const int src = __ffs(crossed) - 1;
+                kstar = 16 * row + 1 + src;
+                qb = __shfl_sync(mask, tot - (int)I, src, 16); // q + prefix before bin k*
+                break;
+            }
+            q = __shfl_sync(mask, tot, 15, 16);
         }
+        const int qq = kstar ? qb : q; // 2^23 <= qq < 2^24: the float sum so far is qq g
+        const double s = __hiloint2double((ex << 20) | ((qq & 0x7FFFFF) >> 3), (qq & 7) << 29);
+        if (!kstar) return s; // the rest of the chain stayed in this binade
+        // bin k* with the reference's own sequence (double add, round to float): next binade
+        r = (double)(float)(s + xr[kstar]);
+        kdone = kstar;
+        if (kstar == 16 * row + 16) row += 1;
     }
-    __device__ __forceinline__ double value() const { return Sp - C; }
-};
+    return r;
+}
 } // namespace
 
 __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams p) {
@@ -142,32 +166,9 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
     double *xhead = reinterpret_cast<double *>(smem + kOffXhead);
     double *heads = reinterpret_cast<double *>(smem + kOffHeads);
     double *xchg_all = reinterpret_cast<double *>(smem + kOffXchg);
-    double *Pall = reinterpret_cast<double *>(smem + kOffP);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kOffBar);
 
     const int tid = threadIdx.x;
-
-    // ============================================================ consumer warp
-    if (tid >= kEnvProducers) {
-        const int lane = tid - kEnvProducers;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int m0 = (tile0 + t) * kEnvH;
-            const int h_cnt = min(kEnvH, sd.n_hops - m0);
-            bar_sync(2, kEnvThreads); // P of tile t is complete
-            if (lane < h_cnt) {
-                const double *Pw = Pall + lane * 257;
-                Chain ch;
-                ch.rebase((double)(float)Pw[0]); // sum_fft = (float)(0 + P[0])
-#pragma unroll 4
-                for (int k = 1; k <= 256; ++k) ch.add(Pw[k]);
-                p.energy[sd.env_off + m0 + lane] = ch.value();
-            }
-            if (t + 1 < n_tiles) bar_arrive(3, kEnvThreads); // P may be overwritten
-        }
-        return;
-    }
-
-    // ============================================================ producer warps
     const short *stream = p.stream + (p.dup ? sd.q_off : sd.pcm_off);
     auto issue_tile = [&](int t) { // one elected thread
         const int m0 = (tile0 + t) * kEnvH;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
         mbar_fence_init();
         issue_tile(0);
     }
-    bar_sync(1, kEnvProducers);
+    __syncthreads();
 
     const int w = tid >> 4, lane16 = tid & 15;
     const unsigned hw_mask = 0xFFFFu << (16 * ((tid >> 4) & 1));
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
                 if ((i & (kHop - 1)) < 16 && (i >> 8) < kEnvH) xhead[(i >> 8) * 16 + (i & 15)] = xv[16 + o];
             }
         }
-        bar_sync(1, kEnvProducers);
+        __syncthreads();
         if (tid == 0 && t + 1 < n_tiles) issue_tile(t + 1); // staging buffer is free: prefetch
 
         // ---- heads: first 16 outputs of windows 1..15 with zero history
@@ -243,12 +244,10 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
             y += fir_tap(0) * (xh[tt] + 0.0);
             heads[w * 16 + tt] = y;
         }
-        bar_sync(1, kEnvProducers);
+        __syncthreads();
 
-        // ---- 16 x 512-point double real FFT, one per half-warp
-        const bool active = w < h_cnt;
-        double pk[8], pq[8], p128 = 0.0; // |X_k|^2 for k = lane16 + 16 d, and for 256 - k
-        if (active) {
+        // ---- 16 x (512-point double real FFT + float-accumulated power), one hop per half-warp
+        if (w < h_cnt) {
             double2 v[16];
 #pragma unroll
             for (int a = 0; a < 16; ++a) v[a] = *reinterpret_cast<const double2 *>(cbuf + w * kHop + 32 * a + 2 * lane16);
@@ -268,14 +267,16 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
             __syncwarp(hw_mask);
 #pragma unroll
             for (int d = 0; d < 8; ++d) bi[d] = xr[(256 - (lane16 + 16 * d)) & 255];
+            __syncwarp(hw_mask);
+            // |X_k|^2, k = 0..256, into the same buffer
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 const int k = lane16 + 16 * d;
                 const double2 A = v[fft16_reg_of(d)];
                 if (k == 0) {
                     const double x0 = A.x + A.y, xn = A.x - A.y; // X_0 and X_256 are real
-                    pk[d] = x0 * x0;
-                    pq[d] = xn * xn;
+                    xr[0] = x0 * x0;
+                    xr[256] = xn * xn;
                 } else {
                     const double2 wk = p.tw2[k];
                     const double sr = A.x + br[d], si = A.y - bi[d];
@@ -284,30 +285,19 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
                     const double ti = dr * wk.y + di * wk.x;
                     const double ar = sr + ti, ai = si - tr;
                     const double cr = sr - ti, ci = si + tr;
-                    pk[d] = 0.25 * (ar * ar + ai * ai);
-                    pq[d] = 0.25 * (cr * cr + ci * ci);
+                    xr[k] = 0.25 * (ar * ar + ai * ai);
+                    xr[256 - k] = 0.25 * (cr * cr + ci * ci);
                 }
             }
             if (lane16 == 0) {
                 const double2 A = v[fft16_reg_of(8)];
-                p128 = A.x * A.x + A.y * A.y;
+                xr[128] = A.x * A.x + A.y * A.y;
             }
+            __syncwarp(hw_mask);
+            const double e = float_chain_scan(xr, lane16, hw_mask);
+            if (lane16 == 0) p.energy[sd.env_off + m0 + w] = e;
         }
-        if (t > 0) bar_sync(3, kEnvThreads); // the consumer has finished with the previous tile's P
-        if (active) {
-            double *P = Pall + w * 257;
-#pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const int k = lane16 + 16 * d;
-                P[k] = pk[d];
-                P[256 - k] = pq[d];
-            }
-            if (lane16 == 0) P[128] = p128;
-        }
-        __threadfence_block();
-        bar_arrive(2, kEnvThreads); // hand P to the consumer
-        // all producers are past their cbuf / heads reads before the next FIR overwrites them
-        bar_sync(1, kEnvProducers);
+        __syncthreads(); // cbuf / heads / xchg free for the next tile
     }
 }
 

@@ -160,6 +160,17 @@ constexpr int kBox = 19;
 __constant__ double c_lp_b[7] = {1.9510e-05, 1.1706e-04, 2.9266e-04, 3.9021e-04, 2.9266e-04, 1.1706e-04, 1.9510e-05};
 __constant__ double c_lp_a[7] = {1.00000, -4.59007, 8.91034, -9.34191, 5.56998, -1.78845, 0.24136};
 
+// x / d for a compile-time constant d, correctly rounded: q = RN(x * (1/d)), one FMA residual, one FMA
+// correction (Markstein). Replaces the ~25-instruction IEEE division in the per-sample loop; the
+// rounding is the division's own for every finite x that is not within a few ulps of the subnormal or
+// overflow range (the envelope samples are O(1)).
+template <int D> __device__ __forceinline__ double div_const(double x) {
+    const double r = 1.0 / (double)D; // RN(1/D), folded at compile time
+    const double q = x * r;
+    const double rem = fma(-(double)D, q, x);
+    return fma(rem, r, q);
+}
+
 struct PeakCounter { // onsets of reference src/tempo_atk_sort.c:277-280, fed one sample at a time
     double prev2, prev1;
     int index_next; // index of the next sample to be pushed
@@ -191,12 +202,10 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
     res.force = 0.0f; res.calm_or_loud = 2; res.beat = 0; res.status = nm.status;
 
     if ((p.what & BLX_DO_ENVELOPE) && nm.status == 0) {
-        const double *E = p.energy + sd.env_off;
+        const double *X = p.xlog + sd.env_off; // log(1 + mu E) / log(1 + mu), from logcomp_kernel
         const int nb = 2 * sd.F;
         const int n2 = 2 * nb;
-        const float mu = 100.0f;
         const float lambda = 0.8f;
-        const double log_den = log((double)(1 + mu));
         const double w_lp = (double)(1 - lambda);
         const double w_df = (double)(lambda * 172);
         const double eps = (double)0.000001f;
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             if (p2 < kBox) {
                 ts2 += v;
             } else {
-                pk.push(ts2 / kBox); // out2[p2 - 10]
+                pk.push(div_const<kBox>(ts2)); // out2[p2 - 10]
                 ts2 -= ring2[r2][tx]; // in2[p2 - 19]
                 ts2 += v;
             }
@@ -228,20 +237,20 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
 
         for (int j = 0; j < n2; ++j) {
             // step 6: log compression, zero-stuffed x2 (reference src/tempo_atk_sort.c:186-190)
-            const double x0 = (j & 1) ? 0.0 : log(1 + (double)mu * E[j >> 1]) / log_den;
+            const double x0 = (j & 1) ? 0.0 : X[j >> 1];
             // step 7: IIR (reference src/tempo_atk_sort.c:201-218)
             double d = 0, c = 0;
             d += c_lp_b[0] * x0; d += c_lp_b[1] * x1; d += c_lp_b[2] * x2; d += c_lp_b[3] * x3;
             d += c_lp_b[4] * x4; d += c_lp_b[5] * x5; d += c_lp_b[6] * x6;
             c += c_lp_a[1] * y1; c += c_lp_a[2] * y2; c += c_lp_a[3] * y3;
             c += c_lp_a[4] * y4; c += c_lp_a[5] * y5; c += c_lp_a[6] * y6;
-            const double y = (d - c) / c_lp_a[0];
+            const double y = d - c; // / buttera[0], which is 1.0 (reference include/bandpass_coeffs.h:489)
             // step 8: rectified difference (reference src/tempo_atk_sort.c:221-226)
             double df;
             if (j == 0) df = y;
             else { df = y - y1; df = (df > 0) ? df : 0; }
             // step 9: weighted mix (reference src/tempo_atk_sort.c:229-232)
-            const double wa = w_lp * y + w_df * df / 10;
+            const double wa = w_lp * y + div_const<10>(w_df * df);
             x6 = x5; x5 = x4; x4 = x3; x3 = x2; x2 = x1; x1 = x0;
             y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
             // step 10: attack sum and the ss array (reference src/tempo_atk_sort.c:246-263)
@@ -257,8 +266,8 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             if (j >= 10) {
                 const int q = j - 10; // index of the filter-1 output becoming final now
                 double o1;
-                if (q <= 8) o1 = ring1[(q % kBox)][tx] / kBox; // untouched entries keep wa[q], then /19
-                else o1 = ts1 / kBox;                          // value before this step's update
+                if (q <= 8) o1 = div_const<kBox>(ring1[q][tx]); // untouched entries keep wa[q], then /19
+                else o1 = div_const<kBox>(ts1);                 // value before this step's update
                 feed2(o1);
             }
             if (j >= kBox) {
@@ -273,17 +282,17 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             // ring1 holds in1[n2-19 .. n2-1]; the oldest is at r1
             double o = ring1[(r1 + 9) % kBox][tx]; // wa[n2 - 10] (== in1 there)
             for (int k = 0; k < kBox; ++k) o += ring1[(r1 + k) % kBox][tx];
-            feed2(o / kBox);
+            feed2(div_const<kBox>(o));
             for (int q = n2 - 9; q < n2; ++q) {
                 const double w = (q == n2 - 1) ? wa_last : ring1[(r1 + (q - (n2 - kBox))) % kBox][tx];
-                feed2(w / kBox);
+                feed2(div_const<kBox>(w));
             }
         }
         // ---- end quirks of filter 2: out2[n2 - 10] = sum of the last 19 inputs, the rest stay 0
         {
             double o = 0;
             for (int k = 0; k < kBox; ++k) o += ring2[(r2 + k) % kBox][tx];
-            pk.push(o / kBox);
+            pk.push(div_const<kBox>(o));
             for (int q = n2 - 9; q < n2; ++q) pk.push(0.0);
         }
         res.beat = pk.beat;
@@ -304,6 +313,24 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
         res.calm_or_loud = (rating > 0) ? 0 : (rating < 0) ? 1 : 2;
     }
     p.out[s] = res;
+}
+
+// Step 6 of the envelope analyser for every hop of every song at once (reference
+// src/tempo_atk_sort.c:186-190): x = log(1 + mu E) / log(1 + mu), mu = 100.0f. Element-wise over the
+// packed energy rows; the sequential tail then only streams x.
+__global__ void logcomp_kernel(const double *__restrict__ energy, double *__restrict__ xlog, long long n) {
+    const float mu = 100.0f;
+    const double log_den = log((double)(1 + mu));
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        xlog[i] = log(1 + (double)mu * energy[i]) / log_den;
+}
+
+cudaError_t launch_logcomp(const double *d_energy, double *d_xlog, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int threads = 256;
+    const long long blocks = (n + threads - 1) / threads;
+    logcomp_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), threads, 0, st>>>(d_energy, d_xlog, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_tail(const TailParams &p, int n_songs, cudaStream_t st) {

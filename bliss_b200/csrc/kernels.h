@@ -44,10 +44,11 @@ cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, 
 struct TailParams {
     const SongDesc *songs;
     const SongNorm *norm;
-    const double *energy;
+    const double *xlog;      // log-compressed energies (launch_logcomp), rows at SongDesc::env_off
     blx_result *out;
     unsigned what;
 };
+cudaError_t launch_logcomp(const double *d_energy, double *d_xlog, long long n, cudaStream_t st);
 cudaError_t launch_tail(const TailParams &p, int n_songs, cudaStream_t st);
 
 cudaError_t launch_distance_rows(const float *d_vectors, int n, int row0, int n_rows, int mode, float *d_out, cudaStream_t st);
