@@ -353,7 +353,7 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         CK(s.hist.reserve((size_t)n * kHistStride * sizeof(unsigned)));
         CK(s.stats.reserve((size_t)n * sizeof(SongStats)));
         CK(s.energy.reserve((size_t)std::max(plan.energy_total, 8ll) * sizeof(double)));
-        CK(s.xlog.reserve((size_t)std::max(plan.energy_total, 8ll) * sizeof(double)));
+        CK(s.xlog.reserve((size_t)(std::max(plan.energy_total, 8ll) + 16) * sizeof(double))); // + read-ahead slack of the tail
         if (plan.kind == kInF32) CK(s.q.reserve((size_t)std::max(plan.q_total, 64ll) * sizeof(short)));
     }
     CK(cudaMemcpyAsync(s.songs.p, s.h_songs, (size_t)n * sizeof(SongDesc), cudaMemcpyHostToDevice, st));

@@ -235,9 +235,8 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             p2++;
         };
 
-        for (int j = 0; j < n2; ++j) {
-            // step 6: log compression, zero-stuffed x2 (reference src/tempo_atk_sort.c:186-190)
-            const double x0 = (j & 1) ? 0.0 : X[j >> 1];
+        // One sample of the chain with every start-up / last-sample condition spelled out.
+        auto step_generic = [&](int j, double x0) {
             // step 7: IIR (reference src/tempo_atk_sort.c:201-218)
             double d = 0, c = 0;
             d += c_lp_b[0] * x0; d += c_lp_b[1] * x1; d += c_lp_b[2] * x2; d += c_lp_b[3] * x3;
@@ -258,11 +257,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             if (j < n2 - 1) { atk_sum += wa; in1 = wa; }
             else { in1 = 0; wa_last = wa; }
             // step 11a: first running-sum filter (out = wa array, in = ss)
-            if (j < kBox) {
-                ts1 += in1;
-            } else {
-                // k = j - 19: out1[k + 9] = ts1 (then /19) is the next input of filter 2 at index j - 10
-            }
+            if (j < kBox) ts1 += in1;
             if (j >= 10) {
                 const int q = j - 10; // index of the filter-1 output becoming final now
                 double o1;
@@ -276,7 +271,56 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             }
             ring1[r1][tx] = in1;
             r1 = (r1 + 1 == kBox) ? 0 : r1 + 1;
+        };
+        // The same sample for 29 <= j < n2 - 1, where both filters are warm and no edge applies:
+        // branch-free, so everything but the IIR recurrence overlaps it. The x history is zero-stuffed
+        // (x1 = x3 = x5 = 0 on even samples, x0 = x2 = x4 = x6 = 0 on odd ones); the skipped products
+        // are exact zeros, so the partial sums are the reference's.
+        auto step_steady = [&](double d) {
+            double c = c_lp_a[1] * y1;
+            c += c_lp_a[2] * y2; c += c_lp_a[3] * y3; c += c_lp_a[4] * y4; c += c_lp_a[5] * y5; c += c_lp_a[6] * y6;
+            const double y = d - c;
+            double df = y - y1;
+            df = (df > 0) ? df : 0;
+            const double wa = w_lp * y + div_const<10>(w_df * df);
+            y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
+            atk_sum += wa;
+            const double o1 = div_const<kBox>(ts1);
+            const double s2 = div_const<kBox>(ts2); // out2[p2 - 10]
+            if (((pk.prev1 - pk.prev2) > eps) && ((pk.prev1 - s2) > eps)) pk.beat++;
+            pk.prev2 = pk.prev1; pk.prev1 = s2; pk.index_next++;
+            ts2 -= ring2[r2][tx]; ts2 += o1;
+            ring2[r2][tx] = o1;
+            r2 = (r2 + 1 == kBox) ? 0 : r2 + 1;
+            p2++;
+            ts1 -= ring1[r1][tx]; ts1 += wa;
+            ring1[r1][tx] = wa;
+            r1 = (r1 + 1 == kBox) ? 0 : r1 + 1;
+        };
+
+        int j = 0;
+        for (; j < 32; ++j) step_generic(j, (j & 1) ? 0.0 : X[j >> 1]); // n2 >= 40 (BLX_SONG_TOO_SHORT otherwise)
+        {
+            // e1, e2, e3: the three most recent even-index inputs (x at j-2, j-4, j-6 for even j)
+            double e1 = x2, e2 = x4, e3 = x6;
+            int i = j >> 1;
+            double q0 = X[i], q1 = X[i + 1], q2 = X[i + 2], q3 = X[i + 3]; // rows carry 16 doubles of slack
+            for (; j + 2 <= n2 - 1; j += 2, ++i) {
+                const double e0 = q0;
+                q0 = q1; q1 = q2; q2 = q3;
+                q3 = X[i + 4]; // used four iterations (8 samples) from now
+                double d = c_lp_b[0] * e0; // even sample
+                d += c_lp_b[2] * e1; d += c_lp_b[4] * e2; d += c_lp_b[6] * e3;
+                step_steady(d);
+                d = c_lp_b[1] * e0; // odd sample
+                d += c_lp_b[3] * e1; d += c_lp_b[5] * e2;
+                step_steady(d);
+                e3 = e2; e2 = e1; e1 = e0;
+            }
+            // back to the generic history: j is even, x1 = 0, x2 = e1, ...
+            x1 = 0; x2 = e1; x3 = 0; x4 = e2; x5 = 0; x6 = e3;
         }
+        for (; j < n2; ++j) step_generic(j, (j & 1) ? 0.0 : X[j >> 1]);
         // ---- end quirks of filter 1 (reference src/tempo_atk_sort.c:34-39): indices n2-10 .. n2-1
         {
             // ring1 holds in1[n2-19 .. n2-1]; the oldest is at r1
