@@ -68,36 +68,80 @@ __global__ void __launch_bounds__(kDistThreads) distance_rows_kernel(const float
     }
 }
 
-// Fused epilogue: nearest other song and row sum, nothing materialised. One warp per row,
-// lanes stride over the columns; ties resolve to the lowest index.
+// Fused epilogue: nearest other song (and optionally the row sum), nothing materialised.
+// CTA = 256 threads x 2 rows each; the column vectors stream through shared memory in tiles of 2048, so
+// every column is read from L2 once per 512 rows and from shared memory as a warp-wide broadcast.
+// The nearest neighbour is decided on the squared distance s (float, reference operation order); the
+// correctly rounded sqrt is taken only for the rare candidates with s <= best s. sqrt is monotone, so a
+// candidate with a larger s can never have a strictly smaller distance; candidates that tie after
+// rounding keep the lowest index (columns are visited in increasing order), exactly what a scan over
+// bl_distance values gives.
+namespace {
+constexpr int kNearRows = 2;
+constexpr int kNearTile = 2048;
+
+__device__ __forceinline__ float sqdist_pair(const float4 a, const float4 b) {
+    const float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y), d2 = __fsub_rn(a.z, b.z), d3 = __fsub_rn(a.w, b.w);
+    float s = __fmul_rn(d0, d0);
+    s = __fadd_rn(s, __fmul_rn(d1, d1));
+    s = __fadd_rn(s, __fmul_rn(d2, d2));
+    s = __fadd_rn(s, __fmul_rn(d3, d3));
+    return s;
+}
+} // namespace
+
+template <bool WITH_SUM>
 __global__ void __launch_bounds__(kDistThreads) distance_nearest_kernel(const float4 *__restrict__ v, int n, int row0,
                                                                         int n_rows, int *__restrict__ idx_out,
                                                                         float *__restrict__ dist_out,
                                                                         double *__restrict__ sum_out) {
-    const int warp = (blockIdx.x * kDistThreads + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_rows) return;
-    const int i = row0 + warp;
-    const float4 a = v[i];
-    float best = __int_as_float(0x7f800000);
-    int best_j = -1;
-    double sum = 0.0;
-    for (int j = lane; j < n; j += 32) {
-        const float d = dist_pair(a, v[j]);
-        sum += (double)d;
-        if (j != i && d < best) { best = d; best_j = j; }
+    __shared__ float4 cols[kNearTile];
+    const float inf = __int_as_float(0x7f800000);
+    int row[kNearRows];
+    float4 a[kNearRows];
+    float best_s[kNearRows], best_d[kNearRows];
+    int best_j[kNearRows];
+    double sum[kNearRows];
+#pragma unroll
+    for (int r = 0; r < kNearRows; ++r) {
+        const int lr = (blockIdx.x * kNearRows + r) * kDistThreads + threadIdx.x; // row inside the slab
+        row[r] = (lr < n_rows) ? row0 + lr : -1;
+        a[r] = (row[r] >= 0) ? v[row[r]] : make_float4(0, 0, 0, 0);
+        best_s[r] = inf; best_d[r] = inf; best_j[r] = -1; sum[r] = 0.0;
+    }
+    for (int c0 = 0; c0 < n; c0 += kNearTile) {
+        const int cn = min(kNearTile, n - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += kDistThreads) cols[i] = v[c0 + i];
+        __syncthreads();
+        float part[kNearRows];
+#pragma unroll
+        for (int r = 0; r < kNearRows; ++r) part[r] = 0.0f;
+#pragma unroll 4
+        for (int i = 0; i < cn; ++i) {
+            const float4 b = cols[i];
+#pragma unroll
+            for (int r = 0; r < kNearRows; ++r) {
+                const float s = sqdist_pair(a[r], b);
+                if (WITH_SUM) part[r] += __fsqrt_rn(s);
+                if (s <= best_s[r] && c0 + i != row[r]) {
+                    const float d = __fsqrt_rn(s);
+                    if (d < best_d[r]) { best_d[r] = d; best_s[r] = s; best_j[r] = c0 + i; }
+                }
+            }
+        }
+        if (WITH_SUM) {
+#pragma unroll
+            for (int r = 0; r < kNearRows; ++r) sum[r] += (double)part[r];
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (oj >= 0 && (ob < best || (ob == best && oj < best_j) || best_j < 0)) { best = ob; best_j = oj; }
-    }
-    if (lane == 0) {
-        if (idx_out) idx_out[warp] = best_j;
-        if (dist_out) dist_out[warp] = best;
-        if (sum_out) sum_out[warp] = sum;
+    for (int r = 0; r < kNearRows; ++r) {
+        if (row[r] < 0) continue;
+        const int o = row[r] - row0;
+        if (idx_out) idx_out[o] = best_j[r];
+        if (dist_out) dist_out[o] = best_d[r];
+        if (WITH_SUM) sum_out[o] = sum[r];
     }
 }
 
@@ -113,9 +157,11 @@ cudaError_t launch_distance_rows(const float *d_vectors, int n, int row0, int n_
 cudaError_t launch_distance_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_dist,
                                     double *d_sum, cudaStream_t st) {
     if (n <= 0 || n_rows <= 0) return cudaSuccess;
-    const int warps_per_cta = kDistThreads / 32;
-    distance_nearest_kernel<<<(n_rows + warps_per_cta - 1) / warps_per_cta, kDistThreads, 0, st>>>(
-        reinterpret_cast<const float4 *>(d_vectors), n, row0, n_rows, d_idx, d_dist, d_sum);
+    const int rows_per_cta = kDistThreads * kNearRows;
+    const unsigned grid = (unsigned)((n_rows + rows_per_cta - 1) / rows_per_cta);
+    const float4 *v = reinterpret_cast<const float4 *>(d_vectors);
+    if (d_sum) distance_nearest_kernel<true><<<grid, kDistThreads, 0, st>>>(v, n, row0, n_rows, d_idx, d_dist, d_sum);
+    else distance_nearest_kernel<false><<<grid, kDistThreads, 0, st>>>(v, n, row0, n_rows, d_idx, d_dist, d_sum);
     return cudaGetLastError();
 }
 

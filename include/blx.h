@@ -117,7 +117,9 @@ int blx_distance_rows_device(blx_engine *e, const float *d_vectors, int n, int r
                              float *d_out, void *stream);
 
 /* Fused epilogue for matrices that cannot be materialised (1 M x 1 M): per row of the
- * slab, the nearest other song and the sum of its distances (a checksum in double). */
+ * slab, the nearest other song (ties to the lowest index, as a scan over bl_distance values) and,
+ * if d_row_sum is not NULL, the sum of the row's distances (a checksum: float partial sums per
+ * 2048-column tile, tiles added in double). Any of the three outputs may be NULL. */
 int blx_distance_nearest_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows,
                                 int *d_nearest_index, float *d_nearest_dist, double *d_row_sum, void *stream);
 

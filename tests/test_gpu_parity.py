@@ -196,7 +196,7 @@ def test_distance_nearest_matches_matrix(engine):
     np.fill_diagonal(dm, np.inf)
     assert np.array_equal(idx.cpu().numpy(), dm.argmin(1))
     assert np.array_equal(dist.cpu().numpy().astype(np.float64), dm.min(1))
-    assert np.allclose(rsum.cpu().numpy(), d.sum(1), rtol=1e-12)
+    assert np.allclose(rsum.cpu().numpy(), d.sum(1), rtol=1e-5)  # float partial sums per column tile
 
 
 # ---------------------------------------------------------------- device-resident entry points
@@ -222,3 +222,21 @@ def test_device_resident_batch_equals_host_batch(engine):
     engine.spectral_device(bliss_b200.FMT_F32, buf.data_ptr(), offs, [len(x) for x in songs], freq.data_ptr(), stream=st)
     torch.cuda.synchronize()
     assert np.array_equal(freq.cpu().numpy(), host["frequency"])
+
+
+def test_parallel_nearest_neighbours_world1(engine, oracle):
+    """bliss_b200.parallel on one rank: nearest neighbour of every song == argmin over bl_distance."""
+    import torch
+    from bliss_b200 import parallel
+    rng = np.random.default_rng(21)
+    v = (rng.standard_normal((3000, 4)) * np.array([5, 3, 8, 6])).astype(np.float32)
+    v[100] = v[2000]  # an exact collision: distance 0, lowest index wins for third parties
+    idx, dst = parallel.nearest_neighbours(engine, torch.from_numpy(v).cuda())
+    torch.cuda.synchronize()
+    d = oracle.distance_matrix(v)
+    np.fill_diagonal(d, np.inf)
+    assert np.array_equal(idx.cpu().numpy(), d.argmin(1))
+    assert np.array_equal(dst.cpu().numpy(), d.min(1))
+    slab = parallel.distance_slab(engine, torch.from_numpy(v[:257]).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(slab.cpu().numpy(), oracle.distance_matrix(v[:257]))
