@@ -42,20 +42,21 @@ namespace {
 constexpr int kEnvThreads = 256;                 // 8 warps = 16 half-warps = 16 FFTs
 constexpr int kEnvH = 16;                        // hops per tile
 constexpr int kTilesPerCta = 8;
-constexpr int kEnvSamples = (kEnvH + 1) * kHop;  // 4352 stream samples per tile
-constexpr int kPerThread = kEnvSamples / kEnvThreads; // 17 consecutive FIR outputs per thread
-static_assert(kPerThread * kEnvThreads == kEnvSamples, "tile must split evenly");
-constexpr int kXr = 17;                          // exchange row stride (doubles)
-constexpr int kXrElems = 16 * kXr;               // 272 doubles per transform
+constexpr int kEnvSamples = (kEnvH + 1) * kHop;  // 4352 stream samples per tile (17 blocks of 256)
+constexpr int kMainOut = 16;                     // FIR outputs per thread in the main pass (blocks 0..15)
+static_assert(kMainOut * kEnvThreads == kEnvH * kHop, "main pass covers 16 blocks");
 
-constexpr int kOffQ = 0;                                   // short[4352]    TMA staging
-constexpr int kOffC = kOffQ + kEnvSamples * 2;             // double[4352]   continuous FIR output
-constexpr int kOffXhead = kOffC + kEnvSamples * 8;         // double[16][16] first 16 inputs of each window
-constexpr int kOffHeads = kOffXhead + 16 * 16 * 8;         // double[16][16] zero-history outputs
-constexpr int kOffXchg = kOffHeads + 16 * 16 * 8;          // double[16][272] exchange, one component at a time
-constexpr int kOffBar = kOffXchg + kEnvH * kXrElems * 8;
+constexpr int kOffQ = 0;                                   // short[4352]     TMA staging (raw int16)
+constexpr int kOffC = kOffQ + kEnvSamples * 2;             // double[4352]    continuous FIR output, swizzled
+constexpr int kOffXchg = kOffC + kEnvSamples * 8;          // double2[16][272] FFT exchange; then |X_k|^2
+constexpr int kOffBar = kOffXchg + kEnvH * kXchgElems * 16;
 constexpr int kEnvSmem = kOffBar + 16;
 static_assert(kEnvSmem <= 115712, "two CTAs per SM");
+
+// The FIR output buffer is addressed in 16-byte cells (two doubles) with an XOR swizzle, so that both
+// the FIR stores (a thread owns 8 consecutive cells) and the FFT loads (a half-warp reads 16
+// consecutive cells, half-warps 128 cells apart) are bank-conflict free.
+__device__ __forceinline__ int cswz(int cell) { return cell ^ ((cell >> 3) & 7); }
 
 // reference include/bandpass_coeffs.h:1-7 — coeffs[0][0..8]; the filter is symmetric.
 __device__ __forceinline__ double fir_tap(int k) {
@@ -64,93 +65,114 @@ __device__ __forceinline__ double fir_tap(int k) {
     return c[k];
 }
 
-// 256-point complex FFT across 16 lanes, exchanging one component at a time through xr
-// (16 x 17 doubles). In: v[a] = z[16 a + lane16]. Out: register r holds Z[lane16 + 16 * fft16_out_index(r)].
-__device__ __forceinline__ void fft256_split(double2 (&v)[16], int lane16, double *xr, const double2 *tw1, unsigned mask) {
-    fft16<double>(v);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const int c = fft16_out_index(r);
-        if (c != 0) v[r] = cmul<double2>(v[r], tw1[c * 16 + lane16]);
-    }
-#pragma unroll
-    for (int r = 0; r < 16; ++r) xr[fft16_out_index(r) * kXr + lane16] = v[r].x;
-    __syncwarp(mask);
-    double re[16];
-#pragma unroll
-    for (int b = 0; b < 16; ++b) re[b] = xr[lane16 * kXr + b];
-    __syncwarp(mask);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) xr[fft16_out_index(r) * kXr + lane16] = v[r].y;
-    __syncwarp(mask);
-#pragma unroll
-    for (int b = 0; b < 16; ++b) {
-        v[b].x = re[b];
-        v[b].y = xr[lane16 * kXr + b];
-    }
-    __syncwarp(mask);
-    fft16<double>(v);
-}
+// Where bin k (0..256) of a hop's power spectrum lives in its exchange buffer: lane b reads its bins
+// 16 b + 1 .. 16 b + 16 at stride 17 doubles (conflict free); bins 0..16 are at their own index.
+__device__ __forceinline__ int pbin(int k) { return k + ((k + 15) >> 4) - 1 + (k == 0); }
 
-// sum_fft of reference src/tempo_atk_sort.c:142-150 for one hop, by the 16 lanes of a half-warp (see
-// the header comment). xr[k] = |X_k|^2, k = 0..256. Returns (double)sum_fft on every lane.
-__device__ __forceinline__ double float_chain_scan(const double *xr, int lane16, unsigned mask) {
-    const int lane_base = (threadIdx.x & 16); // first lane of this half-warp inside its warp
-    // bins 0..16 one by one (the sum climbs through several binades here), every lane redundantly
-    float sf = 0.0f;
+// sum_fft of reference src/tempo_atk_sort.c:142-150 for the two hops of a warp, one per half-warp (see
+// the header comment). xr[pbin(k)] = |X_k|^2 of this lane's half-warp; `active` is false for a
+// half-warp without a hop (last tile of a song). Returns (double)sum_fft on every lane of the half.
+// All 32 lanes run the same control flow, so every shuffle / vote uses the full mask (a partial-mask
+// shuffle compiles to a divergence-safe sequence several times slower); the state of a chain is
+// replicated in the 16 lanes of its half-warp. One loop iteration = one binade: every lane converts
+// its 16 bins, a prefix scan over the half-warp gives all partial sums, the first bin that leaves
+// the binade is located and taken with the reference's double-add / float-convert step.
+__device__ __forceinline__ double float_chain_scan(const double *xr, int lane16, bool active) {
+    const unsigned full = 0xffffffffu;
+    const int lane_base = (threadIdx.x & 16);
+    double pv[16];
 #pragma unroll
-    for (int k = 0; k <= 16; ++k) sf = (float)((double)sf + xr[k]);
-    double r = (double)sf;
+    for (int i = 0; i < 16; ++i) pv[i] = xr[17 * lane16 + 1 + i]; // bins 16 lane16 + 1 + i
+    double r = 0.0;
+    if (active) { // bins 0..16 one by one (the sum climbs through several binades here)
+        float sf = 0.0f;
+#pragma unroll
+        for (int k = 0; k <= 16; ++k) sf = (float)((double)sf + xr[k]);
+        r = (double)sf;
+    }
     int kdone = 16; // bins 0..kdone are in r
-    int row = 1;    // next row of 16 bins: 16 row + 1 .. 16 row + 16
-    while (row < 16) {
+    bool done = !active;
+    while (__any_sync(full, !done)) {
         const int rhi = __double2hiint(r), rlo = __double2loint(r);
         const int ex = (rhi >> 20) & 0x7ff;
-        if (ex < 1023 - 126 || ex > 1023 + 127) {
+        const bool normal = (ex >= 1023 - 126) && (ex <= 1023 + 127);
+        if (!done && !normal) {
             // zero, subnormal, inf or nan: no binade to scan in; one plain reference step
-            r = (double)(float)(r + xr[kdone + 1]);
+            r = (double)(float)(r + xr[pbin(kdone + 1)]);
             kdone += 1;
-            if (kdone == 16 * row + 16) row += 1;
-            continue;
+            if (kdone == 256) done = true;
         }
+        const bool scan = !done && normal;
         // binade e = ex - 1023, float grid g = 2^(e-23); r = q g with 2^23 <= q < 2^24
         const int hiM = ((ex + 29) << 20) | 0x80000; // M = 1.5 * 2^(e+29): ulp(M) = g
         const double M = __hiloint2double(hiM, 0);
-        int q = ((rhi & 0xFFFFF) << 3) | (int)((unsigned)rlo >> 29) | 0x800000;
-        int kstar = 0, qb = 0;
-        for (; row < 16; ++row) {
-            const int k = 16 * row + 1 + lane16;
-            const double t = xr[k] + M; // low word = RN_g(p) / g while p < 2^32 g
-            unsigned I = (__double2hiint(t) == hiM) ? (unsigned)__double2loint(t) : (1u << 25);
-            I = min(I, 1u << 25);
-            if (k <= kdone) I = 0u;
-            int incl = (int)I;
+        const int q = ((rhi & 0xFFFFF) << 3) | (int)((unsigned)rlo >> 29) | 0x800000;
+        int I[16];
+        int lane_sum = 0;
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-                const int up = __shfl_up_sync(mask, incl, o, 16);
-                if (lane16 >= o) incl += up;
-            }
-            const int tot = q + incl;
-            const unsigned crossed = (__ballot_sync(mask, tot >= (1 << 24)) >> lane_base) & 0xFFFFu;
-            if (crossed) {
-                const int src = __ffs(crossed) - 1;
-                kstar = 16 * row + 1 + src;
-                qb = __shfl_sync(mask, tot - (int)I, src, 16); // q + prefix before bin k*
-                break;
-            }
-            q = __shfl_sync(mask, tot, 15, 16);
+        for (int i = 0; i < 16; ++i) {
+            const double t = pv[i] + M; // low word = RN_g(p) / g while p < 2^32 g
+            unsigned v = (__double2hiint(t) == hiM) ? (unsigned)__double2loint(t) : (1u << 25);
+            v = min(v, 1u << 25);
+            I[i] = (scan && (16 * lane16 + 1 + i) > kdone) ? (int)v : 0;
+            lane_sum += I[i];
         }
-        const int qq = kstar ? qb : q; // 2^23 <= qq < 2^24: the float sum so far is qq g
-        const double s = __hiloint2double((ex << 20) | ((qq & 0x7FFFFF) >> 3), (qq & 7) << 29);
-        if (!kstar) return s; // the rest of the chain stayed in this binade
-        // bin k* with the reference's own sequence (double add, round to float): next binade
-        r = (double)(float)(s + xr[kstar]);
-        kdone = kstar;
-        if (kstar == 16 * row + 16) row += 1;
+        lane_sum = min(lane_sum, 1 << 25); // anything >= 2^24 already means "crossed"
+        int incl = lane_sum;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int up = __shfl_up_sync(full, incl, o, 16);
+            if (lane16 >= o) incl += up;
+        }
+        int run = q + incl - lane_sum; // q + prefix before this lane's first bin
+        int idx = 16, before = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int nxt = run + I[i];
+            if (idx == 16 && nxt >= (1 << 24)) { idx = i; before = run; }
+            run = nxt;
+        }
+        const unsigned crossed = (__ballot_sync(full, scan && idx < 16) >> lane_base) & 0xFFFFu;
+        const int src = crossed ? (__ffs(crossed) - 1) : 15;
+        const int sel_idx = __shfl_sync(full, idx, src, 16);
+        const int sel_q = __shfl_sync(full, crossed ? before : run, src, 16);
+        if (scan) {
+            // the float sum before bin k* (or after bin 256) is sel_q g, 2^23 <= sel_q < 2^24
+            const double s = __hiloint2double((ex << 20) | ((sel_q & 0x7FFFFF) >> 3), (sel_q & 7) << 29);
+            if (crossed) {
+                // bin k* with the reference's own sequence (double add, round to float): next binade
+                const int kstar = 16 * src + 1 + sel_idx;
+                r = (double)(float)(s + xr[pbin(kstar)]);
+                kdone = kstar;
+                if (kdone == 256) done = true;
+            } else {
+                r = s;
+                done = true;
+            }
+        }
     }
     return r;
 }
 } // namespace
+
+// Coefficient that multiplies x[j - m] in the 17-tap FIR, m = 0..16 (symmetric; reference
+// include/bandpass_coeffs.h:1-7 and the loop of reference src/tempo_atk_sort.c:124-137).
+__device__ __forceinline__ double fir_coef_of_lag(int m) { return fir_tap(m <= 8 ? m : 16 - m); }
+
+// Output t (0..15) of a window whose delay line starts empty (reference src/tempo_atk_sort.c:121):
+// xs[m] = raw sample at lag m (already 0 where t - m < 0), summed in the reference's order; the
+// affine normalisation only sees the coefficients of the taps inside the window.
+__device__ __forceinline__ double head_output(const double (&xs)[16], int t, double A, double Bm) {
+    double y = 0;
+#pragma unroll
+    for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xs[k] + xs[16 - k]);
+    y += xs[8] * fir_tap(8);
+    y += fir_tap(0) * (xs[0] + 0.0);
+    double csum = 0;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) csum += (m <= t) ? fir_coef_of_lag(m) : 0.0;
+    return fma(y, A, -Bm * csum);
+}
 
 __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -163,20 +185,20 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
 
     short *qs = reinterpret_cast<short *>(smem + kOffQ);
     double *cbuf = reinterpret_cast<double *>(smem + kOffC);
-    double *xhead = reinterpret_cast<double *>(smem + kOffXhead);
-    double *heads = reinterpret_cast<double *>(smem + kOffHeads);
-    double *xchg_all = reinterpret_cast<double *>(smem + kOffXchg);
+    double2 *ccell = reinterpret_cast<double2 *>(smem + kOffC);
+    double2 *xchg_all = reinterpret_cast<double2 *>(smem + kOffXchg);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kOffBar);
 
     const int tid = threadIdx.x;
-    const short *stream = p.stream + (p.dup ? sd.q_off : sd.pcm_off);
+    const int dup = p.dup;
+    const short *stream = p.stream + (dup ? sd.q_off : sd.pcm_off);
     auto issue_tile = [&](int t) { // one elected thread
         const int m0 = (tile0 + t) * kEnvH;
         const int h_cnt = min(kEnvH, sd.n_hops - m0);
         const long long base = (long long)m0 * kHop;
         const int n_need = (h_cnt + 1) * kHop; // always inside the song: (m + 2) * 256 <= 512 F <= n
-        const unsigned bytes = (unsigned)(p.dup ? n_need : 2 * n_need);
-        const short *src = stream + (p.dup ? (base >> 1) : base);
+        const unsigned bytes = (unsigned)(dup ? n_need : 2 * n_need);
+        const short *src = stream + (dup ? (base >> 1) : base);
         fence_proxy_async();
         mbar_arrive_expect_tx(bar, bytes);
         tma_load_1d(qs, src, bytes, bar);
@@ -189,9 +211,15 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
     __syncthreads();
 
     const int w = tid >> 4, lane16 = tid & 15;
-    const unsigned hw_mask = 0xFFFFu << (16 * ((tid >> 4) & 1));
-    const double mean_d = nm.mean_d, inv_var_d = nm.inv_var_d;
-    const int dup = p.dup;
+    // x = (s / 32768 - mean_d) / var_d (reference src/tempo_atk_sort.c:110-113) is affine in the raw
+    // sample s, and the FIR is linear: y = A * (sum c_k s_k) - Bm * (sum c_k), A = 1 / (32768 var_d),
+    // Bm = mean_d / var_d. The taps run over exact integers; one FMA per output normalises.
+    const double A = nm.inv_var_d * (1.0 / 32768);
+    const double Bm = nm.mean_d * nm.inv_var_d;
+    double csum_all = fir_tap(8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) csum_all += 2.0 * fir_tap(k);
+    const double Ball = Bm * csum_all;
     unsigned parity = 0;
 
     for (int t = 0; t < n_tiles; ++t) {
@@ -200,104 +228,146 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
         mbar_wait(bar, parity);
         parity ^= 1u;
 
-        // ---- normalise + continuous FIR, 17 consecutive outputs per thread
+        // ---- continuous FIR, main pass: blocks 0..15, 16 consecutive outputs per thread
         {
-            const int j0 = kPerThread * tid;
-            double xv[16 + kPerThread];
+            const int j0 = kMainOut * tid; // first output; inputs j0 - 16 .. j0 + 15
+            double xv[32];
+            if (dup) { // logical sample i = qs[i >> 1]: 16 shorts give the 32 inputs
+                const int4 *src = reinterpret_cast<const int4 *>(qs + ((j0 - 16) >> 1));
+                int wds[8];
+                if (tid == 0) {
 #pragma unroll
-            for (int i = 0; i < 16 + kPerThread; ++i) {
-                const int idx = j0 - 16 + i;
-                const int ii = idx < 0 ? 0 : idx;
-                // (s / 32768 - mean_d) / var_d, reference src/tempo_atk_sort.c:110-113; the divide is
-                // a multiply by the reciprocal (<= 1 ulp apart)
-                const double s = int_to_double_exact((int)qs[dup ? (ii >> 1) : ii]);
-                const double x = fma(s, 1.0 / 32768, -mean_d) * inv_var_d;
-                xv[i] = (idx < 0) ? 0.0 : x; // delay line starts from zero at the tile start (hop m0's window)
+                    for (int i = 0; i < 8; ++i) wds[i] = 0;
+                } else {
+                    const int4 u0 = src[0], u1 = src[1];
+                    wds[0] = u0.x; wds[1] = u0.y; wds[2] = u0.z; wds[3] = u0.w;
+                    wds[4] = u1.x; wds[5] = u1.y; wds[6] = u1.z; wds[7] = u1.w;
+                }
+                if (tid == 0) { // the tile's own first 16 samples
+                    const int4 u1 = reinterpret_cast<const int4 *>(qs)[0];
+                    wds[4] = u1.x; wds[5] = u1.y; wds[6] = u1.z; wds[7] = u1.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const double lo = int_to_double_exact((int)(short)(wds[i] & 0xffff));
+                    const double hi = int_to_double_exact(wds[i] >> 16);
+                    xv[4 * i] = lo; xv[4 * i + 1] = lo; xv[4 * i + 2] = hi; xv[4 * i + 3] = hi;
+                }
+            } else {
+                const int4 *src = reinterpret_cast<const int4 *>(qs + (j0 - 16));
+                int wds[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int4 u = make_int4(0, 0, 0, 0);
+                    if (tid != 0 || i >= 2) u = src[i]; // the delay line is empty before the tile (never used, see heads)
+                    wds[4 * i] = u.x; wds[4 * i + 1] = u.y; wds[4 * i + 2] = u.z; wds[4 * i + 3] = u.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    xv[2 * i] = int_to_double_exact((int)(short)(wds[i] & 0xffff));
+                    xv[2 * i + 1] = int_to_double_exact(wds[i] >> 16);
+                }
             }
+            double yo[kMainOut];
 #pragma unroll
-            for (int o = 0; o < kPerThread; ++o) {
+            for (int o = 0; o < kMainOut; ++o) {
                 double y = 0;
 #pragma unroll
                 for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xv[o + 16 - k] + xv[o + k]);
                 y += xv[o + 8] * fir_tap(8);
                 y += fir_tap(0) * (xv[o + 16] + xv[o]);
-                cbuf[j0 + o] = y;
-                const int i = j0 + o;
-                if ((i & (kHop - 1)) < 16 && (i >> 8) < kEnvH) xhead[(i >> 8) * 16 + (i & 15)] = xv[16 + o];
+                yo[o] = fma(y, A, -Ball);
             }
-        }
-        __syncthreads();
-        if (tid == 0 && t + 1 < n_tiles) issue_tile(t + 1); // staging buffer is free: prefetch
-
-        // ---- heads: first 16 outputs of windows 1..15 with zero history
-        if (w >= 1) {
-            const double *xh = xhead + w * 16;
-            const int tt = lane16;
-            double y = 0;
 #pragma unroll
-            for (int k = 7; k >= 1; --k) {
-                const double a = (tt - k >= 0) ? xh[tt - k] : 0.0;
-                const double b = (tt - 16 + k >= 0) ? xh[tt - 16 + k] : 0.0;
-                y += fir_tap(k) * (a + b);
+            for (int m = 0; m < 8; ++m) ccell[cswz(8 * tid + m)] = make_double2(yo[2 * m], yo[2 * m + 1]);
+        }
+        // ---- block 16 (second half of the tile's last window): one output per thread
+        {
+            const int j = kEnvH * kHop + tid;
+            double y = 0, xs[17];
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                const int idx = j - 16 + i;
+                xs[i] = int_to_double_exact((int)qs[dup ? (idx >> 1) : idx]);
             }
-            y += ((tt - 8 >= 0) ? xh[tt - 8] : 0.0) * fir_tap(8);
-            y += fir_tap(0) * (xh[tt] + 0.0);
-            heads[w * 16 + tt] = y;
+#pragma unroll
+            for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xs[16 - k] + xs[k]);
+            y += xs[8] * fir_tap(8);
+            y += fir_tap(0) * (xs[16] + xs[0]);
+            cbuf[2 * cswz(j >> 1) + (j & 1)] = fma(y, A, -Ball);
         }
         __syncthreads();
 
-        // ---- 16 x (512-point double real FFT + float-accumulated power), one hop per half-warp
-        if (w < h_cnt) {
-            double2 v[16];
+        // ---- FFT input: 512 FIR outputs of this half-warp's window, the first 16 recomputed with an
+        // empty delay line straight from the raw samples (lanes 0..7 own outputs 2 b, 2 b + 1)
+        double2 v[16];
 #pragma unroll
-            for (int a = 0; a < 16; ++a) v[a] = *reinterpret_cast<const double2 *>(cbuf + w * kHop + 32 * a + 2 * lane16);
-            if (w >= 1 && lane16 < 8) v[0] = *reinterpret_cast<const double2 *>(heads + w * 16 + 2 * lane16);
-            double *xr = xchg_all + w * kXrElems;
-            fft256_split(v, lane16, xr, p.tw1, hw_mask);
-            // even/odd split needs Z[256 - k]: publish Z one component at a time
-            double br[8], bi[8];
+        for (int a = 0; a < 16; ++a) v[a] = ccell[cswz(128 * w + 16 * a + lane16)];
+        if (lane16 < 8) {
+            const int t0 = 2 * lane16; // this lane owns head outputs t0 and t0 + 1
+            const int wbase = kHop * w;
+            auto raw = [&](int i) { // raw sample i of the window, 0 before the window starts
+                const int ii = wbase + (i < 0 ? 0 : i);
+                const double sdbl = int_to_double_exact((int)qs[dup ? (ii >> 1) : ii]);
+                return (i < 0) ? 0.0 : sdbl;
+            };
+            double xs[16];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) xr[lane16 + 16 * fft16_out_index(r)] = v[r].x;
-            __syncwarp(hw_mask);
+            for (int m = 0; m < 16; ++m) xs[m] = raw(t0 - m);
+            const double h0 = head_output(xs, t0, A, Bm);
 #pragma unroll
-            for (int d = 0; d < 8; ++d) br[d] = xr[(256 - (lane16 + 16 * d)) & 255];
-            __syncwarp(hw_mask);
+            for (int m = 15; m >= 1; --m) xs[m] = xs[m - 1];
+            xs[0] = raw(t0 + 1);
+            const double h1 = head_output(xs, t0 + 1, A, Bm);
+            v[0] = make_double2(h0, h1);
+        }
+        __syncthreads(); // FIR buffer and staging buffer are consumed
+        if (tid == 0 && t + 1 < n_tiles) issue_tile(t + 1); // prefetch the next tile
+
+        // ---- 16 x (512-point double real FFT + float-accumulated power), one hop per half-warp;
+        // both half-warps of a warp run in lockstep (an idle one works on stale data and is ignored)
+        if ((w & ~1) < h_cnt) {
+            const unsigned full = 0xffffffffu;
+            double2 *xchg = xchg_all + w * kXchgElems;
+            fft256_halfwarp<double>(v, lane16, xchg, p.tw1, full);
+            __syncwarp(full);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) xr[lane16 + 16 * fft16_out_index(r)] = v[r].y;
-            __syncwarp(hw_mask);
+            for (int r = 0; r < 16; ++r) xchg[lane16 + 16 * fft16_out_index(r)] = v[r];
+            __syncwarp(full);
+            double2 B[8]; // Z[256 - k] for this lane's bins k = lane16 + 16 d
 #pragma unroll
-            for (int d = 0; d < 8; ++d) bi[d] = xr[(256 - (lane16 + 16 * d)) & 255];
-            __syncwarp(hw_mask);
-            // |X_k|^2, k = 0..256, into the same buffer
+            for (int d = 0; d < 8; ++d) B[d] = xchg[(256 - (lane16 + 16 * d)) & 255];
+            __syncwarp(full);
+            double *xr = reinterpret_cast<double *>(xchg); // |X_k|^2, k = 0..256, at pbin(k)
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 const int k = lane16 + 16 * d;
-                const double2 A = v[fft16_reg_of(d)];
+                const double2 Zk = v[fft16_reg_of(d)];
                 if (k == 0) {
-                    const double x0 = A.x + A.y, xn = A.x - A.y; // X_0 and X_256 are real
-                    xr[0] = x0 * x0;
-                    xr[256] = xn * xn;
+                    const double x0 = Zk.x + Zk.y, xn = Zk.x - Zk.y; // X_0 and X_256 are real
+                    xr[pbin(0)] = x0 * x0;
+                    xr[pbin(256)] = xn * xn;
                 } else {
                     const double2 wk = p.tw2[k];
-                    const double sr = A.x + br[d], si = A.y - bi[d];
-                    const double dr = A.x - br[d], di = A.y + bi[d];
+                    const double sr = Zk.x + B[d].x, si = Zk.y - B[d].y;
+                    const double dr = Zk.x - B[d].x, di = Zk.y + B[d].y;
                     const double tr = dr * wk.x - di * wk.y;
                     const double ti = dr * wk.y + di * wk.x;
                     const double ar = sr + ti, ai = si - tr;
                     const double cr = sr - ti, ci = si + tr;
-                    xr[k] = 0.25 * (ar * ar + ai * ai);
-                    xr[256 - k] = 0.25 * (cr * cr + ci * ci);
+                    xr[pbin(k)] = 0.25 * (ar * ar + ai * ai);
+                    xr[pbin(256 - k)] = 0.25 * (cr * cr + ci * ci);
                 }
             }
             if (lane16 == 0) {
-                const double2 A = v[fft16_reg_of(8)];
-                xr[128] = A.x * A.x + A.y * A.y;
+                const double2 Zk = v[fft16_reg_of(8)];
+                xr[pbin(128)] = Zk.x * Zk.x + Zk.y * Zk.y;
             }
-            __syncwarp(hw_mask);
-            const double e = float_chain_scan(xr, lane16, hw_mask);
-            if (lane16 == 0) p.energy[sd.env_off + m0 + w] = e;
+            __syncwarp(full);
+            const double e = float_chain_scan(xr, lane16, w < h_cnt);
+            if (w < h_cnt && lane16 == 0) p.energy[sd.env_off + m0 + w] = e;
         }
-        __syncthreads(); // cbuf / heads / xchg free for the next tile
+        // no barrier here: the next tile's FIR only writes buffers every thread is done with
     }
 }
 
