@@ -58,30 +58,18 @@ template <int KIND> struct P1Smem {
     static constexpr int bytes_full = off_hist + kHistStride * 4;
 };
 
-struct RunHist { // run-length compaction in front of the shared-memory histogram atomics
-    int val;
-    unsigned cnt;
-};
-__device__ __forceinline__ void rh_flush(RunHist &rh, unsigned *hist) {
-    const unsigned bin = (unsigned)(rh.val + 32768 - kHistLo);
-    if (rh.cnt && bin < (unsigned)kHistBins) atomicAdd(&hist[bin], rh.cnt);
-}
-__device__ __forceinline__ void rh_push(RunHist &rh, unsigned *hist, int v, unsigned c) {
-    if (v == rh.val) {
-        rh.cnt += c;
-    } else {
-        rh_flush(rh, hist);
-        rh.val = v;
-        rh.cnt = c;
-    }
+// Histogram of sample values -1904..+1902 (the only bins that can reach the integral of reference
+// src/amplitude_sort.c:69-71): one predicated shared-memory atomic per sample.
+__device__ __forceinline__ void hist_add(unsigned *hist, int v, unsigned c) {
+    const unsigned bin = (unsigned)(v + 32768 - kHistLo);
+    if (bin < (unsigned)kHistBins) atomicAdd(&hist[bin], c);
 }
 
 struct ThreadStats {
-    long long sum;
-    unsigned long long sumsq;
-    int first_nz, last_nz;
+    long long sum;            // sum of samples            (bl_mean, reference src/helpers.c:30-37)
+    unsigned long long sumsq; // sum of squared samples    (bl_variance, reference src/helpers.c:39-49)
+    int first_nz, last_nz;    // reference src/amplitude_sort.c:26-31
 };
-
 } // namespace
 
 template <int KIND, bool FULL>
@@ -104,7 +92,6 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
     const int tid = threadIdx.x;
     const int lane16 = tid & 15;
     const int grp = tid >> 4; // frame slot inside the tile == FFT group
-    const unsigned hw_mask = 0xFFFFu << (16 * ((tid >> 4) & 1));
 
     // ---- one-time setup: tables into shared memory, histogram cleared, barrier armed
     for (int i = tid; i < kWin; i += kP1Threads) hannp[(i >> 5) * 36 + (i & 31)] = p.hann[i];
@@ -155,8 +142,6 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
 
     ThreadStats ts;
     ts.sum = 0; ts.sumsq = 0ull; ts.first_nz = 0x7fffffff; ts.last_nz = -1;
-    RunHist rh;
-    rh.val = 0x40000000; rh.cnt = 0;
 
     unsigned parity = 0;
     int tile = part;
@@ -208,6 +193,9 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
                 w[12 + 4 * i] = b.x; w[12 + 4 * i + 1] = b.y; w[12 + 4 * i + 2] = b.z; w[12 + 4 * i + 3] = b.w;
             }
             short qv[32];
+            int row_sum = 0;
+            unsigned long long row_sq = 0ull;
+            const int valid = (int)max(0ll, min(32ll, n_out - m0)); // samples of this row inside the song
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
 #pragma unroll
@@ -230,16 +218,10 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
                     if (FULL) {
                         const int qi = (int)q;
                         qv[4 * s + u] = (short)qi;
-                        const long long t = m0 + 4 * s + u;
-                        if (t < n_out) {
-                            ts.sum += 2 * qi;
-                            ts.sumsq += 2ull * (unsigned long long)(qi * qi);
-                            if (qi != 0) {
-                                const int i0 = (int)(2 * t);
-                                ts.first_nz = min(ts.first_nz, i0);
-                                ts.last_nz = max(ts.last_nz, i0 + 1);
-                            }
-                            rh_push(rh, hist, qi, 2u);
+                        if (4 * s + u < valid) { // mono sample -> L = R: every value counts twice
+                            row_sum += qi;
+                            row_sq += (unsigned long long)(unsigned)(qi * qi);
+                            hist_add(hist, qi, 2u);
                         }
                     }
                 }
@@ -249,6 +231,22 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
                 *reinterpret_cast<float4 *>(fout + 4 * s) = r4;
 #pragma unroll
                 for (int i = 0; i < 24; ++i) w[i] = w[i + 8];
+            }
+            if (FULL && m0 < n_out) {
+                ts.sum += 2 * (long long)row_sum;
+                ts.sumsq += 2ull * row_sq;
+                // first / last non-zero sample (interleaved index 2 t, 2 t + 1): the row's end samples
+                // decide unless one of them is zero or past the song's end (then scan the row)
+                if (valid == 32 && qv[0] != 0 && qv[31] != 0) {
+                    ts.first_nz = min(ts.first_nz, (int)(2 * m0));
+                    ts.last_nz = max(ts.last_nz, (int)(2 * (m0 + 31) + 1));
+                } else {
+                    for (int i = 0; i < valid; ++i)
+                        if (qv[i] != 0) {
+                            ts.first_nz = min(ts.first_nz, (int)(2 * (m0 + i)));
+                            ts.last_nz = max(ts.last_nz, (int)(2 * (m0 + i) + 1));
+                        }
+                }
             }
             if (FULL && m0 < n_out) { // decimated stream for the envelope pass (mono: L == R)
                 int4 *dst = reinterpret_cast<int4 *>(p.qout + sd.q_off + m0);
@@ -260,6 +258,9 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
             const int4 *rowp = reinterpret_cast<const int4 *>(raw + (size_t)tid * SM::row_stride);
             constexpr int per_vec = (KIND == kInS16Stereo) ? 4 : 8; // per-channel samples per 16-byte load
             const long long i0 = (long long)tile * kP1Threads * G::elems + (long long)tid * G::elems;
+            const int valid_e = (int)max(0ll, min((long long)G::elems, n_elems - i0)); // elements inside the song
+            int row_sum = 0, first_v = 0, last_v = 0;
+            unsigned long long row_sq = 0ull;
 #pragma unroll
             for (int vix = 0; vix < SM::row_bytes / 16; ++vix) {
                 const int4 raw4 = rowp[vix];
@@ -272,20 +273,11 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
                     if (KIND == kInS16Stereo) o[wi] = (float)((lo + hi) / 2); // C truncation toward zero
                     else { o[2 * wi] = (float)lo; o[2 * wi + 1] = (float)hi; }
                     if (FULL) {
-                        const long long ii = i0 + vix * 8 + wi * 2;
-                        const int sv[2] = {lo, hi};
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            if (ii + e < n_elems) {
-                                ts.sum += sv[e];
-                                ts.sumsq += (unsigned long long)(sv[e] * sv[e]);
-                                if (sv[e] != 0) {
-                                    ts.first_nz = min(ts.first_nz, (int)(ii + e));
-                                    ts.last_nz = max(ts.last_nz, (int)(ii + e));
-                                }
-                                rh_push(rh, hist, sv[e], 1u);
-                            }
-                        }
+                        const int e0 = vix * 8 + wi * 2; // element index inside the row
+                        if (e0 < valid_e) { row_sum += lo; row_sq += (unsigned long long)(unsigned)(lo * lo); hist_add(hist, lo, 1u); }
+                        if (e0 + 1 < valid_e) { row_sum += hi; row_sq += (unsigned long long)(unsigned)(hi * hi); hist_add(hist, hi, 1u); }
+                        if (e0 == 0) first_v = lo;
+                        if (e0 + 2 == G::elems) last_v = hi;
                     }
                 }
 #pragma unroll
@@ -298,44 +290,66 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
                     *reinterpret_cast<float4 *>(fout + j) = r4;
                 }
             }
+            if (FULL && valid_e > 0) {
+                ts.sum += row_sum;
+                ts.sumsq += row_sq;
+                // first / last non-zero sample: the row's end samples decide unless one of them is zero
+                // or the row is cut by the song's end (then scan the row)
+                if (valid_e == G::elems && first_v != 0 && last_v != 0) {
+                    ts.first_nz = min(ts.first_nz, (int)i0);
+                    ts.last_nz = max(ts.last_nz, (int)i0 + G::elems - 1);
+                } else {
+                    const short *rs = reinterpret_cast<const short *>(rowp);
+                    for (int i = 0; i < valid_e; ++i)
+                        if (rs[i] != 0) {
+                            ts.first_nz = min(ts.first_nz, (int)i0 + i);
+                            ts.last_nz = max(ts.last_nz, (int)i0 + i);
+                        }
+                }
+            }
         }
         __syncthreads(); // rows consumed, fin complete
 
         // ---- prefetch the next tile of this CTA while the FFTs run
         if (tile + sd.n_parts < sd.n_tiles) issue_tile(tile + sd.n_parts);
 
-        // ---- 8 x (512-point real FFT + power accumulation), 16 threads per frame
-        if (tile * kP1FramesPerTile + grp < sd.n_frames) {
+        // ---- 8 x (512-point real FFT + power accumulation), 16 threads per frame; the two half-warps of
+        // a warp run in lockstep (full-mask syncs), a half-warp past the song's last frame is ignored
+        if (tile * kP1FramesPerTile + (grp & ~1) < sd.n_frames) {
+            const unsigned full = 0xffffffffu;
+            const bool frame_ok = tile * kP1FramesPerTile + grp < sd.n_frames;
             float2 *xchg = reinterpret_cast<float2 *>(fin + grp * kFinFrame);
             float2 v[16];
 #pragma unroll
             for (int a = 0; a < 16; ++a) v[a] = *reinterpret_cast<const float2 *>(fin + grp * kFinFrame + 36 * a + 2 * lane16);
-            __syncwarp(hw_mask);
-            fft256_halfwarp<float>(v, lane16, xchg, tw1, hw_mask);
-            __syncwarp(hw_mask);
+            __syncwarp(full);
+            fft256_halfwarp<float>(v, lane16, xchg, tw1, full);
+            __syncwarp(full);
 #pragma unroll
             for (int r = 0; r < 16; ++r) xchg[lane16 + 16 * fft16_out_index(r)] = v[r];
-            __syncwarp(hw_mask);
+            __syncwarp(full);
+            if (frame_ok) {
 #pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const int k = lane16 + 16 * d;
-                if (k != 0) { // bins k and 512/2 - k from Z[k], Z[256 - k]
-                    const float2 A = v[fft16_reg_of(d)];
-                    const float2 B = xchg[256 - k];
-                    const float2 wk = tw2[k];
-                    const float sr = A.x + B.x, si = A.y - B.y;
-                    const float dr = A.x - B.x, di = A.y + B.y;
-                    const float tr = dr * wk.x - di * wk.y;
-                    const float ti = dr * wk.y + di * wk.x;
-                    const float ar = sr + ti, ai = si - tr;
-                    const float br = sr - ti, bi = si + tr;
-                    accA[d] += 0.25f * (ar * ar + ai * ai);
-                    accB[d] += 0.25f * (br * br + bi * bi);
+                for (int d = 0; d < 8; ++d) {
+                    const int k = lane16 + 16 * d;
+                    if (k != 0) { // bins k and 512/2 - k from Z[k], Z[256 - k]
+                        const float2 A = v[fft16_reg_of(d)];
+                        const float2 B = xchg[256 - k];
+                        const float2 wk = tw2[k];
+                        const float sr = A.x + B.x, si = A.y - B.y;
+                        const float dr = A.x - B.x, di = A.y + B.y;
+                        const float tr = dr * wk.x - di * wk.y;
+                        const float ti = dr * wk.y + di * wk.x;
+                        const float ar = sr + ti, ai = si - tr;
+                        const float br = sr - ti, bi = si + tr;
+                        accA[d] += 0.25f * (ar * ar + ai * ai);
+                        accB[d] += 0.25f * (br * br + bi * bi);
+                    }
                 }
-            }
-            if (lane16 == 0) {
-                const float2 A = v[fft16_reg_of(8)]; // Z[128] -> X[128] = conj(Z[128])
-                acc128 += A.x * A.x + A.y * A.y;
+                if (lane16 == 0) {
+                    const float2 A = v[fft16_reg_of(8)]; // Z[128] -> X[128] = conj(Z[128])
+                    acc128 += A.x * A.x + A.y * A.y;
+                }
             }
         }
         __syncthreads(); // fin / xchg free for the next tile
@@ -359,7 +373,6 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
     }
 
     if (FULL) {
-        rh_flush(rh, hist);
         // statistics: warp shuffle reduction, then one atomic per warp
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
