@@ -231,29 +231,43 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
         // ---- continuous FIR, main pass: blocks 0..15, 16 consecutive outputs per thread
         {
             const int j0 = kMainOut * tid; // first output; inputs j0 - 16 .. j0 + 15
-            double xv[32];
-            if (dup) { // logical sample i = qs[i >> 1]: 16 shorts give the 32 inputs
+            double yo[kMainOut];
+            if (dup) {
+                // The stream is a mono signal u with every sample doubled (L = R): x[2 i] = x[2 i + 1] = u[i].
+                // The 17 taps then fold into two 9-tap filters over u, one for even and one for odd
+                // outputs (same products, summed in a different order than the reference's: ~1e-16).
                 const int4 *src = reinterpret_cast<const int4 *>(qs + ((j0 - 16) >> 1));
                 int wds[8];
-                if (tid == 0) {
+                if (tid == 0) { // the delay line is empty before the tile (those outputs are replaced by the heads)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) wds[i] = 0;
+                    for (int i = 0; i < 4; ++i) wds[i] = 0;
+                    const int4 u1 = reinterpret_cast<const int4 *>(qs)[0];
+                    wds[4] = u1.x; wds[5] = u1.y; wds[6] = u1.z; wds[7] = u1.w;
                 } else {
                     const int4 u0 = src[0], u1 = src[1];
                     wds[0] = u0.x; wds[1] = u0.y; wds[2] = u0.z; wds[3] = u0.w;
                     wds[4] = u1.x; wds[5] = u1.y; wds[6] = u1.z; wds[7] = u1.w;
                 }
-                if (tid == 0) { // the tile's own first 16 samples
-                    const int4 u1 = reinterpret_cast<const int4 *>(qs)[0];
-                    wds[4] = u1.x; wds[5] = u1.y; wds[6] = u1.z; wds[7] = u1.w;
-                }
+                double u[16]; // u[i0 - 8 .. i0 + 7], i0 = j0 / 2
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const double lo = int_to_double_exact((int)(short)(wds[i] & 0xffff));
-                    const double hi = int_to_double_exact(wds[i] >> 16);
-                    xv[4 * i] = lo; xv[4 * i + 1] = lo; xv[4 * i + 2] = hi; xv[4 * i + 3] = hi;
+                    u[2 * i] = int_to_double_exact((int)(short)(wds[i] & 0xffff));
+                    u[2 * i + 1] = int_to_double_exact(wds[i] >> 16);
+                }
+#pragma unroll
+                for (int o = 0; o < 8; ++o) { // outputs 2 (i0 + o) and 2 (i0 + o) + 1; u index of i0 + o is 8 + o
+                    double ye = fir_coef_of_lag(0) * u[8 + o];
+                    double yd = (fir_coef_of_lag(0) + fir_coef_of_lag(1)) * u[8 + o];
+#pragma unroll
+                    for (int m = 1; m <= 8; ++m) {
+                        ye = fma(fir_coef_of_lag(2 * m - 1) + fir_coef_of_lag(2 * m), u[8 + o - m], ye);
+                        yd = fma(fir_coef_of_lag(2 * m) + (m < 8 ? fir_coef_of_lag(2 * m + 1) : 0.0), u[8 + o - m], yd);
+                    }
+                    yo[2 * o] = fma(ye, A, -Ball);
+                    yo[2 * o + 1] = fma(yd, A, -Ball);
                 }
             } else {
+                double xv[32];
                 const int4 *src = reinterpret_cast<const int4 *>(qs + (j0 - 16));
                 int wds[16];
 #pragma unroll
@@ -267,16 +281,15 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
                     xv[2 * i] = int_to_double_exact((int)(short)(wds[i] & 0xffff));
                     xv[2 * i + 1] = int_to_double_exact(wds[i] >> 16);
                 }
-            }
-            double yo[kMainOut];
 #pragma unroll
-            for (int o = 0; o < kMainOut; ++o) {
-                double y = 0;
+                for (int o = 0; o < kMainOut; ++o) {
+                    double y = 0;
 #pragma unroll
-                for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xv[o + 16 - k] + xv[o + k]);
-                y += xv[o + 8] * fir_tap(8);
-                y += fir_tap(0) * (xv[o + 16] + xv[o]);
-                yo[o] = fma(y, A, -Ball);
+                    for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xv[o + 16 - k] + xv[o + k]);
+                    y += xv[o + 8] * fir_tap(8);
+                    y += fir_tap(0) * (xv[o + 16] + xv[o]);
+                    yo[o] = fma(y, A, -Ball);
+                }
             }
 #pragma unroll
             for (int m = 0; m < 8; ++m) ccell[cswz(8 * tid + m)] = make_double2(yo[2 * m], yo[2 * m + 1]);
