@@ -304,11 +304,8 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             // e1, e2, e3: the three most recent even-index inputs (x at j-2, j-4, j-6 for even j)
             double e1 = x2, e2 = x4, e3 = x6;
             int i = j >> 1;
-            double q0 = X[i], q1 = X[i + 1], q2 = X[i + 2], q3 = X[i + 3]; // rows carry 16 doubles of slack
-            for (; j + 2 <= n2 - 1; j += 2, ++i) {
-                const double e0 = q0;
-                q0 = q1; q1 = q2; q2 = q3;
-                q3 = X[i + 4]; // used four iterations (8 samples) from now
+            // one even + one odd sample from the even-index input e0
+            auto pair = [&](double e0) {
                 double d = c_lp_b[0] * e0; // even sample
                 d += c_lp_b[2] * e1; d += c_lp_b[4] * e2; d += c_lp_b[6] * e3;
                 step_steady(d);
@@ -316,7 +313,17 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
                 d += c_lp_b[3] * e1; d += c_lp_b[5] * e2;
                 step_steady(d);
                 e3 = e2; e2 = e1; e1 = e0;
+            };
+            // read-ahead of four inputs (8 samples, ~1000 cycles) in registers that are never moved, so
+            // a load is only waited for when its value is used (rows carry 16 doubles of slack)
+            double q0 = X[i], q1 = X[i + 1], q2 = X[i + 2], q3 = X[i + 3];
+            for (; j + 8 <= n2 - 1; j += 8, i += 4) {
+                double e0 = q0; q0 = X[i + 4]; pair(e0);
+                e0 = q1; q1 = X[i + 5]; pair(e0);
+                e0 = q2; q2 = X[i + 6]; pair(e0);
+                e0 = q3; q3 = X[i + 7]; pair(e0);
             }
+            for (; j + 2 <= n2 - 1; j += 2, ++i) pair(X[i]);
             // back to the generic history: j is even, x1 = 0, x2 = e1, ...
             x1 = 0; x2 = e1; x3 = 0; x4 = e2; x5 = 0; x6 = e3;
         }
