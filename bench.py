@@ -364,7 +364,8 @@ def run_ours(args):
     dom = max(kernels, key=lambda k: kernels[k]["share"])
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        per_song = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        traffic = per_song * B if per_song else None  # bytes per launch (ncu capture scaled to this batch)
     except Exception:
         pass
     if dom == "envelope_kernel":
@@ -510,7 +511,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--songs-per-step", type=int, default=1024)
     ap.add_argument("--seconds", type=float, default=180.0)
-    ap.add_argument("--e2e-songs", type=int, default=128)
+    ap.add_argument("--e2e-songs", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spectral", action="store_true")
     ap.add_argument("--no-distance", action="store_true")

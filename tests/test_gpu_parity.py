@@ -240,3 +240,32 @@ def test_parallel_nearest_neighbours_world1(engine, oracle):
     slab = parallel.distance_slab(engine, torch.from_numpy(v[:257]).cuda())
     torch.cuda.synchronize()
     assert np.array_equal(slab.cpu().numpy(), oracle.distance_matrix(v[:257]))
+
+
+def test_empty_and_tiny_batches(engine):
+    assert len(engine.analyze_s16([], [])) == 0
+    assert len(engine.analyze_f32([])) == 0
+    res = engine.analyze_s16([np.zeros(0, dtype=np.int16), song_s16(3, 2.0)], [0, 2])
+    assert res[0]["status"] & bliss_b200.engine.SONG_TOO_SHORT
+    assert res[1]["status"] == 0
+    assert engine.distance_matrix(np.zeros((0, 4), dtype=np.float32)).shape == (0, 0)
+    one = engine.distance_matrix(np.array([[1, 2, 3, 4]], dtype=np.float32))
+    assert one.shape == (1, 1) and one[0, 0] == 0
+
+
+def test_mono_song_full_analysis(engine, oracle):
+    """channels == 1 through every analyser (reachable by direct calls, reference include/bliss.h:184-217)."""
+    pcm = song_s16(31, 6.0)[::2].copy()
+    res = engine.analyze_s16([pcm], [6], channels=[1])
+    ref = oracle.analyze(pcm, 6, channels=1)
+    check_song(res[0], ref, tag="mono")
+
+
+def test_long_song_envelope_and_counts(engine, oracle):
+    """A 3-minute song (the benchmark length): exact onset count and hop energies."""
+    pcm = song_s16(55, 180.0, decorrelate=True, gain=0.7)
+    res = engine.analyze_s16([pcm], [180])
+    ref = oracle.analyze(pcm, 180)
+    check_song(res[0], ref, tag="3min")
+    E, Eo = engine.envelope_energy(pcm), oracle.envelope_energy(pcm)
+    assert np.max(np.abs(E - Eo) / np.maximum(Eo, 1e-300)) <= 2.4e-7 and np.mean(E == Eo) > 0.99
