@@ -316,23 +316,21 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
         double2 v[16];
 #pragma unroll
         for (int a = 0; a < 16; ++a) v[a] = ccell[cswz(128 * w + 16 * a + lane16)];
-        if (lane16 < 8) {
-            const int t0 = 2 * lane16; // this lane owns head outputs t0 and t0 + 1
+        {
+            // lane t of the half-warp computes head output t; lanes 0..7 then collect outputs 2 b, 2 b + 1
             const int wbase = kHop * w;
-            auto raw = [&](int i) { // raw sample i of the window, 0 before the window starts
-                const int ii = wbase + (i < 0 ? 0 : i);
-                const double sdbl = int_to_double_exact((int)qs[dup ? (ii >> 1) : ii]);
-                return (i < 0) ? 0.0 : sdbl;
-            };
             double xs[16];
 #pragma unroll
-            for (int m = 0; m < 16; ++m) xs[m] = raw(t0 - m);
-            const double h0 = head_output(xs, t0, A, Bm);
-#pragma unroll
-            for (int m = 15; m >= 1; --m) xs[m] = xs[m - 1];
-            xs[0] = raw(t0 + 1);
-            const double h1 = head_output(xs, t0 + 1, A, Bm);
-            v[0] = make_double2(h0, h1);
+            for (int m = 0; m < 16; ++m) { // raw sample at lag m, 0 before the window starts
+                const int i = lane16 - m;
+                const int ii = wbase + (i < 0 ? 0 : i);
+                const double sdbl = int_to_double_exact((int)qs[dup ? (ii >> 1) : ii]);
+                xs[m] = (i < 0) ? 0.0 : sdbl;
+            }
+            const double h = head_output(xs, lane16, A, Bm);
+            const double h0 = __shfl_sync(0xffffffffu, h, (2 * lane16) & 15, 16);
+            const double h1 = __shfl_sync(0xffffffffu, h, (2 * lane16 + 1) & 15, 16);
+            if (lane16 < 8) v[0] = make_double2(h0, h1);
         }
         __syncthreads(); // FIR buffer and staging buffer are consumed
         if (tid == 0 && t + 1 < n_tiles) issue_tile(t + 1); // prefetch the next tile
