@@ -74,9 +74,98 @@ __device__ __forceinline__ int pbin(int k) { return k + ((k + 15) >> 4) - 1 + (k
 // half-warp without a hop (last tile of a song). Returns (double)sum_fft on every lane of the half.
 // All 32 lanes run the same control flow, so every shuffle / vote uses the full mask (a partial-mask
 // shuffle compiles to a divergence-safe sequence several times slower); the state of a chain is
-// replicated in the 16 lanes of its half-warp. One loop iteration = one binade: every lane converts
-// its 16 bins, a prefix scan over the half-warp gives all partial sums, the first bin that leaves
-// the binade is located and taken with the reference's double-add / float-convert step.
+// replicated in the 16 lanes of its half-warp. One loop iteration = one binade:
+//   1. every lane adds up the increments of its own 16 bins (lanes before the current position count
+//      nothing; the one partly consumed lane subtracts what the half-warp measures for its consumed bins),
+//   2. a prefix scan over the 16 lane sums finds the first lane that takes the sum out of the binade,
+//   3. the 16 lanes take one bin of that lane each to find the bin k* itself,
+//   4. bin k* is added with the reference's double-add / float-convert step, which gives the next binade.
+template <bool GUARD>
+__device__ __forceinline__ void chain_round(const double *xr, const double (&pv)[16], int lane16, int lane_base, double &r,
+                                            int &kdone, bool &done) {
+    const unsigned full = 0xffffffffu;
+    const int rhi = __double2hiint(r), rlo = __double2loint(r);
+    const int ex = (rhi >> 20) & 0x7ff;
+    const bool normal = (ex >= 1023 - 126) && (ex <= 1023 + 127);
+    if (!done && !normal) {
+        // zero, subnormal, inf or nan: no binade to scan in; one plain reference step
+        r = (double)(float)(r + xr[pbin(kdone + 1)]);
+        kdone += 1;
+        if (kdone == 256) done = true;
+    }
+    const bool scan = !done && normal;
+    // binade e = ex - 1023, float grid g = 2^(e-23); r = q g with 2^23 <= q < 2^24
+    const int hiM = ((ex + 29) << 20) | 0x80000; // M = 1.5 * 2^(e+29): ulp(M) = g
+    const double M = __hiloint2double(hiM, 0);
+    const int q = ((rhi & 0xFFFFF) << 3) | (int)((unsigned)rlo >> 29) | 0x800000;
+    auto increment = [&](double p) -> int { // RN_g(p) / g (ties follow M's parity)
+        const double t = p + M;
+        unsigned v = (unsigned)__double2loint(t);
+        if (GUARD) { // a bin of 2^25 grid units or more: cap it (it crosses anyway)
+            if (__double2hiint(t) != hiM) v = 1u << 25;
+            v = min(v, 1u << 25);
+        }
+        return (int)v;
+    };
+    // (1) lane sums
+    int lane_sum = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) lane_sum += increment(pv[i]);
+    if (GUARD) lane_sum = min(lane_sum, 1 << 25);
+    const int cur = (kdone - 1) >> 4; // lane that holds bin kdone; its bins up to kdone are consumed
+    {
+        const int kk = 16 * cur + 1 + lane16; // the half-warp measures the consumed part of lane `cur`
+        const int c = (kk <= kdone) ? increment(xr[pbin(kk)]) : 0;
+        const int c_lo = __reduce_add_sync(full, (threadIdx.x & 16) ? 0 : c);
+        const int c_hi = __reduce_add_sync(full, (threadIdx.x & 16) ? c : 0);
+        const int consumed = (threadIdx.x & 16) ? c_hi : c_lo;
+        if (lane16 == cur) lane_sum = GUARD ? max(lane_sum - consumed, 0) : lane_sum - consumed;
+        if (lane16 < cur || !scan) lane_sum = 0;
+    }
+    // (2) first lane that leaves the binade
+    int incl = lane_sum;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int up = __shfl_up_sync(full, incl, o, 16);
+        if (lane16 >= o) incl += up;
+    }
+    const unsigned lanes_over = (__ballot_sync(full, scan && q + incl >= (1 << 24)) >> lane_base) & 0xFFFFu;
+    const int src = lanes_over ? (__ffs(lanes_over) - 1) : 15;
+    const int base = __shfl_sync(full, q + incl - (lanes_over ? lane_sum : 0), src, 16); // sum before lane src
+    if (!__any_sync(full, lanes_over != 0u)) { // both chains of the warp end inside their binades
+        if (scan) {
+            r = __hiloint2double((ex << 20) | ((base & 0x7FFFFF) >> 3), (base & 7) << 29);
+            done = true;
+        }
+        return;
+    }
+    // (3) the bin inside lane src
+    const int kk = 16 * src + 1 + lane16;
+    const int inc1 = (scan && lanes_over && kk > kdone) ? increment(xr[pbin(kk)]) : 0;
+    int incl1 = inc1;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int up = __shfl_up_sync(full, incl1, o, 16);
+        if (lane16 >= o) incl1 += up;
+    }
+    const unsigned bins_over = (__ballot_sync(full, scan && lanes_over && base + incl1 >= (1 << 24)) >> lane_base) & 0xFFFFu;
+    const int bsrc = bins_over ? (__ffs(bins_over) - 1) : 15;
+    const int qb = __shfl_sync(full, base + incl1 - inc1, bsrc, 16); // sum before bin k*
+    // (4)
+    if (scan) {
+        if (lanes_over) {
+            const int kstar = 16 * src + 1 + bsrc;
+            const double sq = __hiloint2double((ex << 20) | ((qb & 0x7FFFFF) >> 3), (qb & 7) << 29);
+            r = (double)(float)(sq + xr[pbin(kstar)]); // reference src/tempo_atk_sort.c:147
+            kdone = kstar;
+            if (kdone == 256) done = true;
+        } else {
+            r = __hiloint2double((ex << 20) | ((base & 0x7FFFFF) >> 3), (base & 7) << 29);
+            done = true;
+        }
+    }
+}
+
 __device__ __forceinline__ double float_chain_scan(const double *xr, int lane16, bool active) {
     const unsigned full = 0xffffffffu;
     const int lane_base = (threadIdx.x & 16);
@@ -90,66 +179,22 @@ __device__ __forceinline__ double float_chain_scan(const double *xr, int lane16,
         for (int k = 0; k <= 16; ++k) sf = (float)((double)sf + xr[k]);
         r = (double)sf;
     }
+    // Largest remaining bin (by its high word, enough for an exponent test): if it is below 2^25 grid
+    // units of the sum after bin 16 it stays so in every later binade: no overflow guard in the rounds.
+    int hmax = 0;
+    if (lane16 != 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hmax = max(hmax, __double2hiint(pv[i]));
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) hmax = max(hmax, __shfl_xor_sync(full, hmax, o, 16));
+    const bool guard = active && ((hmax >> 20) > ((__double2hiint(r) >> 20) & 0x7ff) + 1);
     int kdone = 16; // bins 0..kdone are in r
     bool done = !active;
-    while (__any_sync(full, !done)) {
-        const int rhi = __double2hiint(r), rlo = __double2loint(r);
-        const int ex = (rhi >> 20) & 0x7ff;
-        const bool normal = (ex >= 1023 - 126) && (ex <= 1023 + 127);
-        if (!done && !normal) {
-            // zero, subnormal, inf or nan: no binade to scan in; one plain reference step
-            r = (double)(float)(r + xr[pbin(kdone + 1)]);
-            kdone += 1;
-            if (kdone == 256) done = true;
-        }
-        const bool scan = !done && normal;
-        // binade e = ex - 1023, float grid g = 2^(e-23); r = q g with 2^23 <= q < 2^24
-        const int hiM = ((ex + 29) << 20) | 0x80000; // M = 1.5 * 2^(e+29): ulp(M) = g
-        const double M = __hiloint2double(hiM, 0);
-        const int q = ((rhi & 0xFFFFF) << 3) | (int)((unsigned)rlo >> 29) | 0x800000;
-        int I[16];
-        int lane_sum = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const double t = pv[i] + M; // low word = RN_g(p) / g while p < 2^32 g
-            unsigned v = (__double2hiint(t) == hiM) ? (unsigned)__double2loint(t) : (1u << 25);
-            v = min(v, 1u << 25);
-            I[i] = (scan && (16 * lane16 + 1 + i) > kdone) ? (int)v : 0;
-            lane_sum += I[i];
-        }
-        lane_sum = min(lane_sum, 1 << 25); // anything >= 2^24 already means "crossed"
-        int incl = lane_sum;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const int up = __shfl_up_sync(full, incl, o, 16);
-            if (lane16 >= o) incl += up;
-        }
-        int run = q + incl - lane_sum; // q + prefix before this lane's first bin
-        int idx = 16, before = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int nxt = run + I[i];
-            if (idx == 16 && nxt >= (1 << 24)) { idx = i; before = run; }
-            run = nxt;
-        }
-        const unsigned crossed = (__ballot_sync(full, scan && idx < 16) >> lane_base) & 0xFFFFu;
-        const int src = crossed ? (__ffs(crossed) - 1) : 15;
-        const int sel_idx = __shfl_sync(full, idx, src, 16);
-        const int sel_q = __shfl_sync(full, crossed ? before : run, src, 16);
-        if (scan) {
-            // the float sum before bin k* (or after bin 256) is sel_q g, 2^23 <= sel_q < 2^24
-            const double s = __hiloint2double((ex << 20) | ((sel_q & 0x7FFFFF) >> 3), (sel_q & 7) << 29);
-            if (crossed) {
-                // bin k* with the reference's own sequence (double add, round to float): next binade
-                const int kstar = 16 * src + 1 + sel_idx;
-                r = (double)(float)(s + xr[pbin(kstar)]);
-                kdone = kstar;
-                if (kdone == 256) done = true;
-            } else {
-                r = s;
-                done = true;
-            }
-        }
+    if (__any_sync(full, guard)) {
+        while (__any_sync(full, !done)) chain_round<true>(xr, pv, lane16, lane_base, r, kdone, done);
+    } else {
+        while (__any_sync(full, !done)) chain_round<false>(xr, pv, lane16, lane_base, r, kdone, done);
     }
     return r;
 }
