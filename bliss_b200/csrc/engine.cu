@@ -279,7 +279,7 @@ static void plan_songs(int fmt, const long long *offsets, const long long *lengt
     const int tile_m = pass1_tile_msamples();
     // A song is cut into parts of kTilesPerPart consecutive tiles, one CTA each. The cut depends on the
     // song alone, so its partial spectra (and their float summation order) are the same in any batch.
-    const int kTilesPerPart = 16;
+    const int kTilesPerPart = 64;
     plan->kind = (fmt == BLX_FMT_F32) ? kInF32 : channels_kind;
     long long env = 0, q = 0;
     int parts = 0;
