@@ -7,8 +7,8 @@
 Workload (config.workload): the per-GPU share of BASELINE.json configs[2] — synthetic 3-minute
 44.1 kHz mono float32 songs through the FULL bl_analyze pipeline (front-end, amplitude, frequency,
 envelope/tempo/attack, rating). One "step" = one pass of the pipeline over one batch of
-`--songs-per-step` songs that is already resident in HBM (32.5 GB at the default 1024, far larger
-than the 126 MB L2, so no flush is needed between steps). 8 steps of 1024 = the 8 192 songs one GPU
+`--songs-per-step` songs that is already resident in HBM (65 GB at the default 2048, far larger
+than the 126 MB L2, so no flush is needed between steps). 4 steps of 2048 = the 8 192 songs one GPU
 owns in configs[2]. Songs shard across ranks with no data-path collective ("scaling": "weak").
 
 One JSON line on stdout (rank 0). Beyond the base contract it carries
@@ -467,7 +467,20 @@ def run_ours(args):
             if len(d):
                 log(f"  field {k}: {len(d)} songs differ, e.g. song {d[0]}: host {out_host[k][d[0]]!r} device {res[k][d[0]]!r}")
         raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
-    e2e = {"value": world * Be * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": world * Be * n_in * 4,
+    # raw pinned host -> device bandwidth of this box, for context: the e2e path is PCIe-bound
+    probe_n = min(Be, 64) * stride
+    dprobe = torch.empty(probe_n, dtype=torch.float32, device=dev)
+    dprobe.copy_(pinned[:probe_n], non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(3):
+        dprobe.copy_(pinned[:probe_n], non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * probe_n * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del dprobe
+    e2e = {"value": world * Be * e2e_steps / e2e_s, "unit": UNIT, "h2d_achieved_gbs": Be * e2e_steps * n_in * 4 / e2e_s / 1e9,
+           "h2d_memcpy_peak_gbs": h2d_gbs, "h2d_bytes_per_step": world * Be * n_in * 4,
            "d2h_bytes_per_step": world * Be * 32, "songs_per_step": world * Be, "steps": e2e_steps,
            "api": "blx_analyze_batch_f32 (include/blx.h), pinned host PCM"}
 
@@ -506,10 +519,10 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--songs-per-step", type=int, default=1024)
+    ap.add_argument("--songs-per-step", type=int, default=2048)
     ap.add_argument("--seconds", type=float, default=180.0)
     ap.add_argument("--e2e-songs", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")

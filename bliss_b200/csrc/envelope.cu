@@ -41,7 +41,7 @@ namespace blx {
 namespace {
 constexpr int kEnvThreads = 256;                 // 8 warps = 16 half-warps = 16 FFTs
 constexpr int kEnvH = 16;                        // hops per tile
-constexpr int kTilesPerCta = 8;
+constexpr int kTilesPerCta = 16;
 constexpr int kEnvSamples = (kEnvH + 1) * kHop;  // 4352 stream samples per tile (17 blocks of 256)
 constexpr int kMainOut = 16;                     // FIR outputs per thread in the main pass (blocks 0..15)
 static_assert(kMainOut * kEnvThreads == kEnvH * kHop, "main pass covers 16 blocks");
