@@ -8,11 +8,19 @@
 //   - sum |X_k|^2, k = 0..256, in a FLOAT accumulator in bin order (reference :142-149).
 //
 // Design. For j - window_start >= 16 the restarted FIR equals the continuous
-// FIR of the stream (same operands, same order), so a tile of 16 consecutive hops computes the
-// continuous FIR ONCE per sample (17 blocks of 256 samples) and only the first 16 outputs of each
-// window ("heads") separately with zero history. Then 16 FFTs run at once, 16 threads each
-// (fft16.cuh, double). A CTA walks kTilesPerCta tiles; the int16 tile of t+1 is fetched by one 1-D
-// bulk copy (cp.async.bulk / UBLKCP) as soon as the FIR of tile t has consumed the staging buffer.
+// FIR of the stream (same operands), so the continuous FIR is computed ONCE per sample, in blocks
+// of 256 samples that live in a ring of 17 shared-memory slots: a tile of 16 hops adds 16 new
+// blocks (the block shared with the previous tile is still in the ring; the first tile of a CTA
+// is preceded by a one-block prologue pass). The first 16 outputs of every window ("heads") are
+// the continuous outputs minus the contribution of the 16 samples before the window, a 16 x 16
+// triangular product that the 16 lanes of the hop's half-warp evaluate from a coefficient table.
+// Then 16 FFTs run at once, 16 threads each (fft16.cuh, double). A CTA walks kTilesPerCta tiles;
+// the int16 samples of tile t + 1 are fetched by one 1-D bulk copy (cp.async.bulk / UBLKCP) as
+// soon as tile t has consumed the staging buffer.
+//
+// DUP = true: the stream is a mono signal u with every sample doubled (L = R), stored once
+// (x[2 i] = x[2 i + 1] = u[i], the decimated stream pass 1 writes for float32 input). The 17 taps
+// then fold into two 9-tap filters over u, one for even and one for odd outputs.
 //
 // The float accumulation s <- (float)((double)s + p_k), k = 0..256, is a chain of 257 dependent
 // roundings (~50-75 cycles each on the FP64 + conversion pipes): run naively it idles the SM. It is
@@ -29,9 +37,9 @@
 // rounding midpoint (the reference rounds to double, then to float; exact ties follow the parity of
 // the magic constant instead of q).
 //
-// FP64 throughout; the summation order of the FIR is the reference's. FMA contraction is allowed
-// here (the reference has none): it perturbs E[m] by ~1e-16 relative, nine orders of magnitude
-// below the 1e-7 onset-count cliff measured in SURVEY.md App. B.
+// FP64 throughout. FMA contraction and the folded / corrected summation orders differ from the
+// reference's (which has no FMA) by ~1e-16 relative in E[m], nine orders of magnitude below the
+// 1e-7 onset-count cliff measured in SURVEY.md App. B.
 #include "blx_common.cuh"
 #include "fft16.cuh"
 #include "kernels.h"
@@ -42,21 +50,28 @@ namespace {
 constexpr int kEnvThreads = 256;                 // 8 warps = 16 half-warps = 16 FFTs
 constexpr int kEnvH = 16;                        // hops per tile
 constexpr int kTilesPerCta = 16;
-constexpr int kEnvSamples = (kEnvH + 1) * kHop;  // 4352 stream samples per tile (17 blocks of 256)
-constexpr int kMainOut = 16;                     // FIR outputs per thread in the main pass (blocks 0..15)
-static_assert(kMainOut * kEnvThreads == kEnvH * kHop, "main pass covers 16 blocks");
+constexpr int kRingSlots = kEnvH + 1;            // FIR blocks resident in shared memory
+constexpr int kSlotBytes = kHop * 8;             // one block of 256 FIR outputs (128 cells of 16 bytes)
 
-constexpr int kOffQ = 0;                                   // short[4352]     TMA staging (raw int16)
-constexpr int kOffC = kOffQ + kEnvSamples * 2;             // double[4352]    continuous FIR output, swizzled
-constexpr int kOffXchg = kOffC + kEnvSamples * 8;          // double2[16][272] FFT exchange; then |X_k|^2
-constexpr int kOffBar = kOffXchg + kEnvH * kXchgElems * 16;
-constexpr int kEnvSmem = kOffBar + 16;
-static_assert(kEnvSmem <= 115712, "two CTAs per SM");
-
-// The FIR output buffer is addressed in 16-byte cells (two doubles) with an XOR swizzle, so that both
-// the FIR stores (a thread owns 8 consecutive cells) and the FFT loads (a half-warp reads 16
-// consecutive cells, half-warps 128 cells apart) are bank-conflict free.
-__device__ __forceinline__ int cswz(int cell) { return cell ^ ((cell >> 3) & 7); }
+// Shared-memory plan. Raw samples: a lead-in of one block (only its first `pre` elements are used:
+// the samples before the tile's first window, carried over from the previous pass), then the staging
+// area the bulk copy fills: s[i] = stream element blk * (G + 1) - pre + i, G = first block of the tile.
+template <bool DUP> struct EG {
+    static constexpr int pre = DUP ? 8 : 16;     // raw elements in front of a block that its FIR reads
+    static constexpr int blk = DUP ? 128 : 256;  // raw elements per block
+    static constexpr int blk_bytes = blk * 2;
+    static constexpr int per_thread = blk / 16;  // raw elements whose outputs one thread computes
+    static constexpr int taps = DUP ? 8 : 16;    // head-correction terms per lane
+    static constexpr int row = taps + 2;         // doubles per head-table row: taps, D, pad
+    static constexpr int off_q = 0;
+    static constexpr int q_bytes = blk_bytes + kEnvH * blk_bytes + 128;
+    static constexpr int off_ring = off_q + q_bytes;                       // double[17][256], swizzled cells
+    static constexpr int off_xchg = off_ring + kRingSlots * kSlotBytes;    // double2[16][272] FFT exchange; then |X_k|^2
+    static constexpr int off_tab = off_xchg + kEnvH * kXchgElems * 16;     // double[16][row] head table
+    static constexpr int off_bar = off_tab + 16 * row * 8;
+    static constexpr int bytes = off_bar + 16;
+    static_assert(bytes <= 115712, "two CTAs per SM");
+};
 
 // reference include/bandpass_coeffs.h:1-7 — coeffs[0][0..8]; the filter is symmetric.
 __device__ __forceinline__ double fir_tap(int k) {
@@ -64,6 +79,19 @@ __device__ __forceinline__ double fir_tap(int k) {
                              0.0580037,  -0.0779167, 0.0882711, 0.9065095};
     return c[k];
 }
+// Coefficient that multiplies x[j - m] in the 17-tap FIR, m = 0..16 (symmetric; reference
+// include/bandpass_coeffs.h:1-7 and the loop of reference src/tempo_atk_sort.c:124-137).
+__device__ __forceinline__ double fir_coef_of_lag(int m) { return fir_tap(m <= 8 ? m : 16 - m); }
+// Folded taps of the doubled mono stream: even output 2 n = sum_m fold_e(m) u[n - m], odd output
+// 2 n + 1 = sum_m fold_d(m) u[n - m], m = 0..8.
+__device__ __forceinline__ double fold_e(int m) { return m == 0 ? fir_coef_of_lag(0) : fir_coef_of_lag(2 * m - 1) + fir_coef_of_lag(2 * m); }
+__device__ __forceinline__ double fold_d(int m) { return fir_coef_of_lag(2 * m) + (m < 8 ? fir_coef_of_lag(2 * m + 1) : 0.0); }
+// the same three functions with a run-time argument (table set-up only)
+__constant__ double c_fir_half[9] = {-0.0023470, 0.0044613, -0.0114627, 0.0226382, -0.0405147,
+                                     0.0580037,  -0.0779167, 0.0882711, 0.9065095};
+__device__ __forceinline__ double fir_coef_rt(int m) { return c_fir_half[m <= 8 ? m : 16 - m]; }
+__device__ __forceinline__ double fold_e_rt(int m) { return m == 0 ? fir_coef_rt(0) : fir_coef_rt(2 * m - 1) + fir_coef_rt(2 * m); }
+__device__ __forceinline__ double fold_d_rt(int m) { return fir_coef_rt(2 * m) + (m < 8 ? fir_coef_rt(2 * m + 1) : 0.0); }
 
 // Where bin k (0..256) of a hop's power spectrum lives in its exchange buffer: lane b reads its bins
 // 16 b + 1 .. 16 b + 16 at stride 17 doubles (conflict free); bins 0..16 are at their own index.
@@ -198,28 +226,15 @@ __device__ __forceinline__ double float_chain_scan(const double *xr, int lane16,
     }
     return r;
 }
+
+// Ring cell (16 bytes = two consecutive FIR outputs) c of a block, XOR-swizzled so that both the FIR
+// stores (a thread owns 8 consecutive cells) and the FFT loads (a half-warp reads 16 consecutive
+// cells) are bank-conflict free.
+__device__ __forceinline__ int cswz(int cell) { return cell ^ ((cell >> 3) & 7); }
 } // namespace
 
-// Coefficient that multiplies x[j - m] in the 17-tap FIR, m = 0..16 (symmetric; reference
-// include/bandpass_coeffs.h:1-7 and the loop of reference src/tempo_atk_sort.c:124-137).
-__device__ __forceinline__ double fir_coef_of_lag(int m) { return fir_tap(m <= 8 ? m : 16 - m); }
-
-// Output t (0..15) of a window whose delay line starts empty (reference src/tempo_atk_sort.c:121):
-// xs[m] = raw sample at lag m (already 0 where t - m < 0), summed in the reference's order; the
-// affine normalisation only sees the coefficients of the taps inside the window.
-__device__ __forceinline__ double head_output(const double (&xs)[16], int t, double A, double Bm) {
-    double y = 0;
-#pragma unroll
-    for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xs[k] + xs[16 - k]);
-    y += xs[8] * fir_tap(8);
-    y += fir_tap(0) * (xs[0] + 0.0);
-    double csum = 0;
-#pragma unroll
-    for (int m = 0; m < 16; ++m) csum += (m <= t) ? fir_coef_of_lag(m) : 0.0;
-    return fma(y, A, -Bm * csum);
-}
-
-__global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams p) {
+template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams p) {
+    using G = EG<DUP>;
     extern __shared__ __align__(128) unsigned char smem[];
     const SongDesc sd = p.songs[blockIdx.y];
     const int tile0 = blockIdx.x * kTilesPerCta;
@@ -228,34 +243,75 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
     if (nm.status != 0) return;
     const int n_tiles = min(kTilesPerCta, (sd.n_hops - tile0 * kEnvH + kEnvH - 1) / kEnvH);
 
-    short *qs = reinterpret_cast<short *>(smem + kOffQ);
-    double *cbuf = reinterpret_cast<double *>(smem + kOffC);
-    double2 *ccell = reinterpret_cast<double2 *>(smem + kOffC);
-    double2 *xchg_all = reinterpret_cast<double2 *>(smem + kOffXchg);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kOffBar);
+    unsigned char *qs = smem + G::off_q;
+    unsigned char *ring = smem + G::off_ring;
+    double2 *xchg_all = reinterpret_cast<double2 *>(smem + G::off_xchg);
+    double *tab = reinterpret_cast<double *>(smem + G::off_tab);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + G::off_bar);
 
     const int tid = threadIdx.x;
-    const int dup = p.dup;
-    const short *stream = p.stream + (dup ? sd.q_off : sd.pcm_off);
-    auto issue_tile = [&](int t) { // one elected thread
-        const int m0 = (tile0 + t) * kEnvH;
-        const int h_cnt = min(kEnvH, sd.n_hops - m0);
-        const long long base = (long long)m0 * kHop;
-        const int n_need = (h_cnt + 1) * kHop; // always inside the song: (m + 2) * 256 <= 512 F <= n
-        const unsigned bytes = (unsigned)(dup ? n_need : 2 * n_need);
-        const short *src = stream + (dup ? (base >> 1) : base);
+    const short *stream = p.stream + (DUP ? sd.q_off : sd.pcm_off);
+    const int g0 = tile0 * kEnvH; // first block (= first hop) of this CTA
+    // Pass t (one elected thread): t >= 0 stages the raw samples of blocks G + 1 .. G + h_cnt, G = g0 + 16 t,
+    // with `pre` elements in front; the prologue t = -1 stages block g0 where thread group 15 expects it.
+    auto issue_pass = [&](int t) {
+        long long e0;   // first stream element
+        int dst, bytes;
+        if (t < 0) {
+            e0 = (long long)G::blk * g0 - G::pre;
+            dst = G::blk_bytes + 15 * G::blk_bytes;
+            bytes = (G::blk + G::pre) * 2;
+            if (g0 == 0) { e0 = 0; dst += G::pre * 2; bytes = G::blk * 2; } // nothing before the song: zeros (set below)
+        } else {
+            const int m0 = g0 + t * kEnvH;
+            const int h_cnt = min(kEnvH, sd.n_hops - m0);
+            e0 = (long long)G::blk * (m0 + 1) - G::pre;
+            dst = G::blk_bytes;
+            bytes = (h_cnt * G::blk + G::pre) * 2; // inside the song: (m + 2) * 256 <= 512 F <= n
+        }
         fence_proxy_async();
-        mbar_arrive_expect_tx(bar, bytes);
-        tma_load_1d(qs, src, bytes, bar);
+        mbar_arrive_expect_tx(bar, (unsigned)bytes);
+        tma_load_1d(qs + dst, stream + e0, (unsigned)bytes, bar);
     };
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
-        issue_tile(0);
+        if (g0 == 0) {
+            int4 *z = reinterpret_cast<int4 *>(qs + G::blk_bytes + 15 * G::blk_bytes);
+            z[0] = make_int4(0, 0, 0, 0);
+            if (!DUP) z[1] = make_int4(0, 0, 0, 0);
+        }
+        issue_pass(-1);
+    }
+    const int hw = tid >> 4, lane16 = tid & 15;
+    // Head table: a window's output t (its first 16) lacks the terms of the `pre` raw samples X[0..pre)
+    // in front of the window; row `lane16` holds the coefficients of those terms for the output this
+    // lane corrects, then the sum of the dropped coefficients (for the mean term).
+    //   DUP: lane = n + 8 part, output 2 n + part: sum_{j >= n} fold(8 + n - j) X[j]
+    //   else: lane = output j:                      sum_{i >= j} c(j + 16 - i) X[i]
+    if (tid < 16) {
+        double *trow = tab + tid * G::row;
+        double dsum = 0.0;
+        if (DUP) {
+            const int n = tid & 7, part = tid >> 3;
+            for (int j = 0; j < 8; ++j) {
+                const int m = 8 + n - j;
+                const double c = (j >= n) ? (part ? fold_d_rt(m) : fold_e_rt(m)) : 0.0;
+                trow[j] = c;
+                dsum += c;
+            }
+        } else {
+            for (int i = 0; i < 16; ++i) {
+                const double c = (i >= tid) ? fir_coef_rt(tid + 16 - i) : 0.0;
+                trow[i] = c;
+                dsum += c;
+            }
+        }
+        trow[G::taps] = dsum;
+        trow[G::taps + 1] = 0.0;
     }
     __syncthreads();
 
-    const int w = tid >> 4, lane16 = tid & 15;
     // x = (s / 32768 - mean_d) / var_d (reference src/tempo_atk_sort.c:110-113) is affine in the raw
     // sample s, and the FIR is linear: y = A * (sum c_k s_k) - Bm * (sum c_k), A = 1 / (32768 var_d),
     // Bm = mean_d / var_d. The taps run over exact integers; one FMA per output normalises.
@@ -267,67 +323,53 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
     const double Ball = Bm * csum_all;
     unsigned parity = 0;
 
-    for (int t = 0; t < n_tiles; ++t) {
-        const int m0 = (tile0 + t) * kEnvH;
-        const int h_cnt = min(kEnvH, sd.n_hops - m0);
+    for (int t = -1; t < n_tiles; ++t) {
         mbar_wait(bar, parity);
         parity ^= 1u;
 
-        // ---- continuous FIR, main pass: blocks 0..15, 16 consecutive outputs per thread
-        {
-            const int j0 = kMainOut * tid; // first output; inputs j0 - 16 .. j0 + 15
-            double yo[kMainOut];
-            if (dup) {
-                // The stream is a mono signal u with every sample doubled (L = R): x[2 i] = x[2 i + 1] = u[i].
-                // The 17 taps then fold into two 9-tap filters over u, one for even and one for odd
-                // outputs (same products, summed in a different order than the reference's: ~1e-16).
-                const int4 *src = reinterpret_cast<const int4 *>(qs + ((j0 - 16) >> 1));
-                int wds[8];
-                if (tid == 0) { // the delay line is empty before the tile (those outputs are replaced by the heads)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) wds[i] = 0;
-                    const int4 u1 = reinterpret_cast<const int4 *>(qs)[0];
-                    wds[4] = u1.x; wds[5] = u1.y; wds[6] = u1.z; wds[7] = u1.w;
-                } else {
-                    const int4 u0 = src[0], u1 = src[1];
-                    wds[0] = u0.x; wds[1] = u0.y; wds[2] = u0.z; wds[3] = u0.w;
-                    wds[4] = u1.x; wds[5] = u1.y; wds[6] = u1.z; wds[7] = u1.w;
-                }
-                double u[16]; // u[i0 - 8 .. i0 + 7], i0 = j0 / 2
+        // ---- continuous FIR: thread group hw computes block 16 t + 1 + hw (relative to g0), every thread
+        // 16 consecutive outputs (8 cells); in the prologue only group 15 works (block 0)
+        if (t >= 0 || hw == 15) {
+            const unsigned char *sp = qs + G::blk_bytes + tid * (G::per_thread * 2); // s[per_thread * tid ...]
+            double yo[16];
+            if (DUP) {
+                // inputs u[k] = s[8 tid + k], k = 0..15; output pair o uses u[8 + o - m], m = 0..8
+                const int4 u0 = reinterpret_cast<const int4 *>(sp)[0], u1 = reinterpret_cast<const int4 *>(sp)[1];
+                const int wds[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                double u[16];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     u[2 * i] = int_to_double_exact((int)(short)(wds[i] & 0xffff));
                     u[2 * i + 1] = int_to_double_exact(wds[i] >> 16);
                 }
 #pragma unroll
-                for (int o = 0; o < 8; ++o) { // outputs 2 (i0 + o) and 2 (i0 + o) + 1; u index of i0 + o is 8 + o
-                    double ye = fir_coef_of_lag(0) * u[8 + o];
-                    double yd = (fir_coef_of_lag(0) + fir_coef_of_lag(1)) * u[8 + o];
+                for (int o = 0; o < 8; ++o) {
+                    double ye = fold_e(0) * u[8 + o];
+                    double yd = fold_d(0) * u[8 + o];
 #pragma unroll
                     for (int m = 1; m <= 8; ++m) {
-                        ye = fma(fir_coef_of_lag(2 * m - 1) + fir_coef_of_lag(2 * m), u[8 + o - m], ye);
-                        yd = fma(fir_coef_of_lag(2 * m) + (m < 8 ? fir_coef_of_lag(2 * m + 1) : 0.0), u[8 + o - m], yd);
+                        ye = fma(fold_e(m), u[8 + o - m], ye);
+                        yd = fma(fold_d(m), u[8 + o - m], yd);
                     }
                     yo[2 * o] = fma(ye, A, -Ball);
                     yo[2 * o + 1] = fma(yd, A, -Ball);
                 }
             } else {
+                // inputs xv[k] = s[16 tid + k], k = 0..31; output o uses xv[o + 16 - m], m = 0..16, summed in
+                // the reference's order (reference src/tempo_atk_sort.c:124-137)
                 double xv[32];
-                const int4 *src = reinterpret_cast<const int4 *>(qs + (j0 - 16));
-                int wds[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    int4 u = make_int4(0, 0, 0, 0);
-                    if (tid != 0 || i >= 2) u = src[i]; // the delay line is empty before the tile (never used, see heads)
-                    wds[4 * i] = u.x; wds[4 * i + 1] = u.y; wds[4 * i + 2] = u.z; wds[4 * i + 3] = u.w;
+                    const int4 q4 = reinterpret_cast<const int4 *>(sp)[i];
+                    const int wds[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        xv[8 * i + 2 * j] = int_to_double_exact((int)(short)(wds[j] & 0xffff));
+                        xv[8 * i + 2 * j + 1] = int_to_double_exact(wds[j] >> 16);
+                    }
                 }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    xv[2 * i] = int_to_double_exact((int)(short)(wds[i] & 0xffff));
-                    xv[2 * i + 1] = int_to_double_exact(wds[i] >> 16);
-                }
-#pragma unroll
-                for (int o = 0; o < kMainOut; ++o) {
+                for (int o = 0; o < 16; ++o) {
                     double y = 0;
 #pragma unroll
                     for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xv[o + 16 - k] + xv[o + k]);
@@ -336,49 +378,66 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
                     yo[o] = fma(y, A, -Ball);
                 }
             }
+            const int rb = 16 * t + 1 + hw; // 0 .. 256
+            unsigned char *slot = ring + (rb % kRingSlots) * kSlotBytes + 128 * lane16;
+            const int key = 16 * (lane16 & 7);
 #pragma unroll
-            for (int m = 0; m < 8; ++m) ccell[cswz(8 * tid + m)] = make_double2(yo[2 * m], yo[2 * m + 1]);
-        }
-        // ---- block 16 (second half of the tile's last window): one output per thread
-        {
-            const int j = kEnvH * kHop + tid;
-            double y = 0, xs[17];
-#pragma unroll
-            for (int i = 0; i < 17; ++i) {
-                const int idx = j - 16 + i;
-                xs[i] = int_to_double_exact((int)qs[dup ? (idx >> 1) : idx]);
-            }
-#pragma unroll
-            for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xs[16 - k] + xs[k]);
-            y += xs[8] * fir_tap(8);
-            y += fir_tap(0) * (xs[16] + xs[0]);
-            cbuf[2 * cswz(j >> 1) + (j & 1)] = fma(y, A, -Ball);
+            for (int m = 0; m < 8; ++m)
+                *reinterpret_cast<double2 *>(slot + ((16 * m) ^ key)) = make_double2(yo[2 * m], yo[2 * m + 1]);
         }
         __syncthreads();
 
-        // ---- FFT input: 512 FIR outputs of this half-warp's window, the first 16 recomputed with an
-        // empty delay line straight from the raw samples (lanes 0..7 own outputs 2 b, 2 b + 1)
+        const int m0 = g0 + (t < 0 ? 0 : t) * kEnvH;
+        const int h_cnt = (t < 0) ? 0 : min(kEnvH, sd.n_hops - m0);
+        const int w = hw; // hop of this half-warp inside the tile
         double2 v[16];
+        if (t >= 0) {
+            // ---- FFT input: the 512 FIR outputs of this half-warp's window (blocks 16 t + w and the next) ...
+            const int sa = (16 * t + w) % kRingSlots;
+            const int sb = (sa + 1 == kRingSlots) ? 0 : sa + 1;
+            const unsigned char *ba = ring + sa * kSlotBytes, *bb = ring + sb * kSlotBytes;
 #pragma unroll
-        for (int a = 0; a < 16; ++a) v[a] = ccell[cswz(128 * w + 16 * a + lane16)];
-        {
-            // lane t of the half-warp computes head output t; lanes 0..7 then collect outputs 2 b, 2 b + 1
-            const int wbase = kHop * w;
-            double xs[16];
-#pragma unroll
-            for (int m = 0; m < 16; ++m) { // raw sample at lag m, 0 before the window starts
-                const int i = lane16 - m;
-                const int ii = wbase + (i < 0 ? 0 : i);
-                const double sdbl = int_to_double_exact((int)qs[dup ? (ii >> 1) : ii]);
-                xs[m] = (i < 0) ? 0.0 : sdbl;
+            for (int a = 0; a < 8; ++a) {
+                v[a] = *reinterpret_cast<const double2 *>(ba + 16 * cswz(16 * a + lane16));
+                v[a + 8] = *reinterpret_cast<const double2 *>(bb + 16 * cswz(16 * a + lane16));
             }
-            const double h = head_output(xs, lane16, A, Bm);
-            const double h0 = __shfl_sync(0xffffffffu, h, (2 * lane16) & 15, 16);
-            const double h1 = __shfl_sync(0xffffffffu, h, (2 * lane16 + 1) & 15, 16);
-            if (lane16 < 8) v[0] = make_double2(h0, h1);
+            // ... whose first 16 see an empty delay line: take out the terms of the raw samples in front of
+            // the window (head table above) and put back the mean term of the dropped coefficients
+            const unsigned char *hp = qs + G::blk_bytes * w; // w = 0: carried over from the previous pass
+            const double *trow = tab + lane16 * G::row;
+            double X[G::taps];
+#pragma unroll
+            for (int i = 0; i < G::taps / 8; ++i) {
+                const int4 q4 = reinterpret_cast<const int4 *>(hp)[i];
+                const int wds[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    X[8 * i + 2 * j] = int_to_double_exact((int)(short)(wds[j] & 0xffff));
+                    X[8 * i + 2 * j + 1] = int_to_double_exact(wds[j] >> 16);
+                }
+            }
+            double corr = 0.0;
+#pragma unroll
+            for (int i = 0; i < G::taps; i += 2) {
+                const double2 c2 = *reinterpret_cast<const double2 *>(trow + i);
+                corr = fma(c2.x, X[i], corr);
+                corr = fma(c2.y, X[i + 1], corr);
+            }
+            const double h = fma(Bm, trow[G::taps], -(A * corr));
+            const int s0 = DUP ? lane16 : 2 * lane16, s1 = DUP ? lane16 + 8 : 2 * lane16 + 1;
+            const double h0 = __shfl_sync(0xffffffffu, h, s0 & 15, 16);
+            const double h1 = __shfl_sync(0xffffffffu, h, s1 & 15, 16);
+            if (lane16 < 8) { v[0].x += h0; v[0].y += h1; }
         }
-        __syncthreads(); // FIR buffer and staging buffer are consumed
-        if (tid == 0 && t + 1 < n_tiles) issue_tile(t + 1); // prefetch the next tile
+        __syncthreads(); // ring blocks and raw samples are consumed
+        if (tid == 0) {
+            // the `pre` raw samples in front of the next tile's first window, then the next tile
+            const int4 *cs = reinterpret_cast<const int4 *>(qs + G::blk_bytes + 15 * G::blk_bytes);
+            int4 *cd = reinterpret_cast<int4 *>(qs);
+            cd[0] = cs[0];
+            if (!DUP) cd[1] = cs[1];
+            if (t + 1 < n_tiles) issue_pass(t + 1);
+        }
 
         // ---- 16 x (512-point double real FFT + float-accumulated power), one hop per half-warp;
         // both half-warps of a warp run in lockstep (an idle one works on stale data and is ignored)
@@ -423,21 +482,24 @@ __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams
             const double e = float_chain_scan(xr, lane16, w < h_cnt);
             if (w < h_cnt && lane16 == 0) p.energy[sd.env_off + m0 + w] = e;
         }
-        // no barrier here: the next tile's FIR only writes buffers every thread is done with
+        // no barrier here: the next pass only writes ring blocks and raw samples every thread is done with
     }
 }
 
 cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(envelope_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEnvSmem);
+        cudaError_t e = cudaFuncSetAttribute(envelope_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<true>::bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(envelope_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<false>::bytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     if (max_hops <= 0) return cudaSuccess;
     const int per_cta = kEnvH * kTilesPerCta;
     dim3 grid((unsigned)((max_hops + per_cta - 1) / per_cta), (unsigned)n_songs);
-    envelope_kernel<<<grid, kEnvThreads, kEnvSmem, st>>>(p);
+    if (p.dup) envelope_kernel<true><<<grid, kEnvThreads, EG<true>::bytes, st>>>(p);
+    else envelope_kernel<false><<<grid, kEnvThreads, EG<false>::bytes, st>>>(p);
     return cudaGetLastError();
 }
 
