@@ -9,14 +9,16 @@
 //
 // Design. For j - window_start >= 16 the restarted FIR equals the continuous
 // FIR of the stream (same operands), so the continuous FIR is computed ONCE per sample, in blocks
-// of 256 samples that live in a ring of 17 shared-memory slots: a tile of 16 hops adds 16 new
-// blocks (the block shared with the previous tile is still in the ring; the first tile of a CTA
-// is preceded by a one-block prologue pass). The first 16 outputs of every window ("heads") are
-// the continuous outputs minus the contribution of the 16 samples before the window, a 16 x 16
-// triangular product that the 16 lanes of the hop's half-warp evaluate from a coefficient table.
-// Then 16 FFTs run at once, 16 threads each (fft16.cuh, double). A CTA walks kTilesPerCta tiles;
-// the int16 samples of tile t + 1 are fetched by one 1-D bulk copy (cp.async.bulk / UBLKCP) as
-// soon as tile t has consumed the staging buffer.
+// of 256 samples. Every WARP works on its own: it owns a run of consecutive hops and walks it two
+// hops (= two new FIR blocks) at a time; the block shared with the previous pair stays in a
+// per-warp carry slot. The first 16 outputs of every window ("heads") are the continuous outputs
+// minus the contribution of the 16 samples before the window, a 16 x 16 triangular product that
+// the 16 lanes of the hop's half-warp evaluate from a coefficient table. Then the two FFTs of the
+// pair run at once, 16 lanes each (fft16.cuh, double), followed by the float-accumulated power
+// sum. The raw int16 samples of the next pair are fetched by the warp's own 1-D bulk copy
+// (cp.async.bulk / UBLKCP, one mbarrier per buffer) while the FFTs of the current pair run. There
+// is no block-wide barrier after set-up, so the warps of an SM drift apart and the FP64-bound
+// phases (FIR, FFT) of some overlap the latency-bound phase (accumulation chain) of others.
 //
 // DUP = true: the stream is a mono signal u with every sample doubled (L = R), stored once
 // (x[2 i] = x[2 i + 1] = u[i], the decimated stream pass 1 writes for float32 input). The 17 taps
@@ -47,29 +49,31 @@
 namespace blx {
 
 namespace {
-constexpr int kEnvThreads = 256;                 // 8 warps = 16 half-warps = 16 FFTs
-constexpr int kEnvH = 16;                        // hops per tile
-constexpr int kTilesPerCta = 16;
-constexpr int kRingSlots = kEnvH + 1;            // FIR blocks resident in shared memory
+constexpr int kEnvThreads = 256;                 // 8 independent warps
+constexpr int kEnvWarps = kEnvThreads / 32;
+constexpr int kPairsPerWarp = 16;                // a warp owns 32 consecutive hops
+constexpr int kHopsPerCta = 2 * kPairsPerWarp * kEnvWarps;
 constexpr int kSlotBytes = kHop * 8;             // one block of 256 FIR outputs (128 cells of 16 bytes)
 
-// Shared-memory plan. Raw samples: a lead-in of one block (only its first `pre` elements are used:
-// the samples before the tile's first window, carried over from the previous pass), then the staging
-// area the bulk copy fills: s[i] = stream element blk * (G + 1) - pre + i, G = first block of the tile.
+// Shared-memory plan. Per warp: the FFT exchange buffers of its two hops (whose first 4 KB first hold
+// the two new FIR blocks of the pair), the carry block, two raw-sample buffers and their mbarriers.
+// A raw buffer holds r[i] = stream element blk * (B + 1) - pre + i, B = first block (= hop) of the pair:
+// `pre` samples in front, then the two new blocks.
 template <bool DUP> struct EG {
     static constexpr int pre = DUP ? 8 : 16;     // raw elements in front of a block that its FIR reads
     static constexpr int blk = DUP ? 128 : 256;  // raw elements per block
     static constexpr int blk_bytes = blk * 2;
-    static constexpr int per_thread = blk / 16;  // raw elements whose outputs one thread computes
+    static constexpr int per_thread = blk / 16;  // raw elements whose outputs one lane computes
     static constexpr int taps = DUP ? 8 : 16;    // head-correction terms per lane
     static constexpr int row = taps + 2;         // doubles per head-table row: taps, D, pad
-    static constexpr int off_q = 0;
-    static constexpr int q_bytes = blk_bytes + kEnvH * blk_bytes + 128;
-    static constexpr int off_ring = off_q + q_bytes;                       // double[17][256], swizzled cells
-    static constexpr int off_xchg = off_ring + kRingSlots * kSlotBytes;    // double2[16][272] FFT exchange; then |X_k|^2
-    static constexpr int off_tab = off_xchg + kEnvH * kXchgElems * 16;     // double[16][row] head table
-    static constexpr int off_bar = off_tab + 16 * row * 8;
-    static constexpr int bytes = off_bar + 16;
+    static constexpr int raw_bytes = ((pre + 2 * blk) * 2 + 63) / 64 * 64;
+    static constexpr int w_xchg = 0;                                  // double2[2][272]; FIR blocks B+1, B+2 at +0, +2048
+    static constexpr int w_carry = w_xchg + 2 * kXchgElems * 16;      // FIR block B
+    static constexpr int w_raw = w_carry + kSlotBytes;                // 2 raw buffers
+    static constexpr int w_bar = w_raw + 2 * raw_bytes;               // 2 mbarriers
+    static constexpr int w_bytes = (w_bar + 16 + 127) / 128 * 128;
+    static constexpr int off_tab = kEnvWarps * w_bytes;               // double[16][row] head table
+    static constexpr int bytes = off_tab + 16 * row * 8;
     static_assert(bytes <= 115712, "two CTAs per SM");
 };
 
@@ -237,53 +241,14 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
     using G = EG<DUP>;
     extern __shared__ __align__(128) unsigned char smem[];
     const SongDesc sd = p.songs[blockIdx.y];
-    const int tile0 = blockIdx.x * kTilesPerCta;
-    if (tile0 * kEnvH >= sd.n_hops) return;
+    if (blockIdx.x * kHopsPerCta >= sd.n_hops) return;
     const SongNorm nm = p.norm[blockIdx.y];
     if (nm.status != 0) return;
-    const int n_tiles = min(kTilesPerCta, (sd.n_hops - tile0 * kEnvH + kEnvH - 1) / kEnvH);
-
-    unsigned char *qs = smem + G::off_q;
-    unsigned char *ring = smem + G::off_ring;
-    double2 *xchg_all = reinterpret_cast<double2 *>(smem + G::off_xchg);
-    double *tab = reinterpret_cast<double *>(smem + G::off_tab);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + G::off_bar);
 
     const int tid = threadIdx.x;
-    const short *stream = p.stream + (DUP ? sd.q_off : sd.pcm_off);
-    const int g0 = tile0 * kEnvH; // first block (= first hop) of this CTA
-    // Pass t (one elected thread): t >= 0 stages the raw samples of blocks G + 1 .. G + h_cnt, G = g0 + 16 t,
-    // with `pre` elements in front; the prologue t = -1 stages block g0 where thread group 15 expects it.
-    auto issue_pass = [&](int t) {
-        long long e0;   // first stream element
-        int dst, bytes;
-        if (t < 0) {
-            e0 = (long long)G::blk * g0 - G::pre;
-            dst = G::blk_bytes + 15 * G::blk_bytes;
-            bytes = (G::blk + G::pre) * 2;
-            if (g0 == 0) { e0 = 0; dst += G::pre * 2; bytes = G::blk * 2; } // nothing before the song: zeros (set below)
-        } else {
-            const int m0 = g0 + t * kEnvH;
-            const int h_cnt = min(kEnvH, sd.n_hops - m0);
-            e0 = (long long)G::blk * (m0 + 1) - G::pre;
-            dst = G::blk_bytes;
-            bytes = (h_cnt * G::blk + G::pre) * 2; // inside the song: (m + 2) * 256 <= 512 F <= n
-        }
-        fence_proxy_async();
-        mbar_arrive_expect_tx(bar, (unsigned)bytes);
-        tma_load_1d(qs + dst, stream + e0, (unsigned)bytes, bar);
-    };
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        if (g0 == 0) {
-            int4 *z = reinterpret_cast<int4 *>(qs + G::blk_bytes + 15 * G::blk_bytes);
-            z[0] = make_int4(0, 0, 0, 0);
-            if (!DUP) z[1] = make_int4(0, 0, 0, 0);
-        }
-        issue_pass(-1);
-    }
-    const int hw = tid >> 4, lane16 = tid & 15;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int hw = lane >> 4, lane16 = lane & 15; // half-warp = hop of the pair
+    double *tab = reinterpret_cast<double *>(smem + G::off_tab);
     // Head table: a window's output t (its first 16) lacks the terms of the `pre` raw samples X[0..pre)
     // in front of the window; row `lane16` holds the coefficients of those terms for the output this
     // lane corrects, then the sum of the dropped coefficients (for the mean term).
@@ -310,7 +275,54 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
         trow[G::taps] = dsum;
         trow[G::taps + 1] = 0.0;
     }
-    __syncthreads();
+
+    unsigned char *wsm = smem + warp * G::w_bytes;
+    double2 *xchg = reinterpret_cast<double2 *>(wsm + G::w_xchg) + hw * kXchgElems;
+    unsigned char *newblk = wsm + G::w_xchg; // FIR blocks B + 1, B + 2 of the pair (consumed before the FFT exchange)
+    unsigned char *carry = wsm + G::w_carry; // FIR block B
+    unsigned char *raw = wsm + G::w_raw;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + G::w_bar);
+
+    const int B0 = blockIdx.x * kHopsPerCta + warp * (2 * kPairsPerWarp); // first hop (= first block) of this warp
+    const int n_mine = min(2 * kPairsPerWarp, sd.n_hops - B0);            // hops of this warp
+    const int n_pairs = (n_mine + 1) >> 1;
+    const short *stream = p.stream + (DUP ? sd.q_off : sd.pcm_off);
+    // Pass q (lane 0): q >= 0 stages the raw samples of the new blocks of pair q; the prologue q = -1 stages
+    // block B0 where the upper half-warp expects it. Buffer = q & 1.
+    auto issue_pass = [&](int q) {
+        unsigned char *dst = raw + (q & 1) * G::raw_bytes;
+        long long e0;
+        int bytes;
+        if (q < 0) {
+            e0 = (long long)G::blk * B0 - G::pre;
+            dst += G::blk_bytes;
+            bytes = (G::blk + G::pre) * 2;
+            if (B0 == 0) { e0 = 0; dst += G::pre * 2; bytes = G::blk * 2; } // nothing before the song: zeros (set below)
+        } else {
+            const int nb = min(2, n_mine - 2 * q); // new blocks this pair needs; (m + 2) * 256 <= 512 F <= n
+            e0 = (long long)G::blk * (B0 + 2 * q + 1) - G::pre;
+            bytes = (nb * G::blk + G::pre) * 2;
+        }
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar + (q & 1), (unsigned)bytes);
+        tma_load_1d(dst, stream + e0, (unsigned)bytes, bar + (q & 1));
+    };
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_fence_init();
+        if (n_mine > 0) {
+            if (B0 == 0) {
+                int4 *z = reinterpret_cast<int4 *>(raw + G::raw_bytes + G::blk_bytes);
+                z[0] = make_int4(0, 0, 0, 0);
+                if (!DUP) z[1] = make_int4(0, 0, 0, 0);
+            }
+            issue_pass(-1);
+            issue_pass(0);
+        }
+    }
+    __syncthreads(); // the only block-wide barrier: table and mbarriers are set up
+    if (n_mine <= 0) return;
 
     // x = (s / 32768 - mean_d) / var_d (reference src/tempo_atk_sort.c:110-113) is affine in the raw
     // sample s, and the FIR is linear: y = A * (sum c_k s_k) - Bm * (sum c_k), A = 1 / (32768 var_d),
@@ -321,19 +333,24 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
 #pragma unroll
     for (int k = 0; k < 8; ++k) csum_all += 2.0 * fir_tap(k);
     const double Ball = Bm * csum_all;
-    unsigned parity = 0;
+    const unsigned full = 0xffffffffu;
+    const int key = 16 * (lane16 & 7);
+    // byte offset of ring cell 16 a + lane16 inside a block: 256 a + 16 (lane16 ^ ((2 a + (lane16 >> 3)) & 7))
+    int coff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) coff[i] = 16 * (lane16 ^ ((2 * i + (lane16 >> 3)) & 7));
 
-    for (int t = -1; t < n_tiles; ++t) {
-        mbar_wait(bar, parity);
-        parity ^= 1u;
+    for (int q = -1; q < n_pairs; ++q) {
+        const unsigned char *rcur = raw + (q & 1) * G::raw_bytes;
+        mbar_wait(bar + (q & 1), (unsigned)((q + 1) >> 1) & 1u);
 
-        // ---- continuous FIR: thread group hw computes block 16 t + 1 + hw (relative to g0), every thread
-        // 16 consecutive outputs (8 cells); in the prologue only group 15 works (block 0)
-        if (t >= 0 || hw == 15) {
-            const unsigned char *sp = qs + G::blk_bytes + tid * (G::per_thread * 2); // s[per_thread * tid ...]
+        // ---- continuous FIR: half-warp hw computes block B + 1 + hw, every lane 16 consecutive outputs
+        // (8 cells); in the prologue only the upper half-warp's block (B0) is kept
+        {
+            const unsigned char *sp = rcur + lane * (G::per_thread * 2); // r[per_thread * lane ...]
             double yo[16];
             if (DUP) {
-                // inputs u[k] = s[8 tid + k], k = 0..15; output pair o uses u[8 + o - m], m = 0..8
+                // inputs u[k] = r[8 lane + k], k = 0..15; output pair o uses u[8 + o - m], m = 0..8
                 const int4 u0 = reinterpret_cast<const int4 *>(sp)[0], u1 = reinterpret_cast<const int4 *>(sp)[1];
                 const int wds[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
                 double u[16];
@@ -355,7 +372,7 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                     yo[2 * o + 1] = fma(yd, A, -Ball);
                 }
             } else {
-                // inputs xv[k] = s[16 tid + k], k = 0..31; output o uses xv[o + 16 - m], m = 0..16, summed in
+                // inputs xv[k] = r[16 lane + k], k = 0..31; output o uses xv[o + 16 - m], m = 0..16, summed in
                 // the reference's order (reference src/tempo_atk_sort.c:124-137)
                 double xv[32];
 #pragma unroll
@@ -378,32 +395,32 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                     yo[o] = fma(y, A, -Ball);
                 }
             }
-            const int rb = 16 * t + 1 + hw; // 0 .. 256
-            unsigned char *slot = ring + (rb % kRingSlots) * kSlotBytes + 128 * lane16;
-            const int key = 16 * (lane16 & 7);
+            unsigned char *slot = ((q < 0) ? carry : newblk + hw * kSlotBytes) + 128 * lane16;
+            if (q >= 0 || hw == 1) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m)
-                *reinterpret_cast<double2 *>(slot + ((16 * m) ^ key)) = make_double2(yo[2 * m], yo[2 * m + 1]);
+                for (int m = 0; m < 8; ++m)
+                    *reinterpret_cast<double2 *>(slot + ((16 * m) ^ key)) = make_double2(yo[2 * m], yo[2 * m + 1]);
+            }
         }
-        __syncthreads();
+        __syncwarp(full);
+        if (q < 0) continue;
 
-        const int m0 = g0 + (t < 0 ? 0 : t) * kEnvH;
-        const int h_cnt = (t < 0) ? 0 : min(kEnvH, sd.n_hops - m0);
-        const int w = hw; // hop of this half-warp inside the tile
+        // ---- FFT input: the 512 FIR outputs of this half-warp's window: blocks B, B + 1 (hop 0) or
+        // B + 1, B + 2 (hop 1) ...
         double2 v[16];
-        if (t >= 0) {
-            // ---- FFT input: the 512 FIR outputs of this half-warp's window (blocks 16 t + w and the next) ...
-            const int sa = (16 * t + w) % kRingSlots;
-            const int sb = (sa + 1 == kRingSlots) ? 0 : sa + 1;
-            const unsigned char *ba = ring + sa * kSlotBytes, *bb = ring + sb * kSlotBytes;
+        {
+            const unsigned char *ba = hw ? newblk : carry, *bb = newblk + hw * kSlotBytes;
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
-                v[a] = *reinterpret_cast<const double2 *>(ba + 16 * cswz(16 * a + lane16));
-                v[a + 8] = *reinterpret_cast<const double2 *>(bb + 16 * cswz(16 * a + lane16));
+                v[a] = *reinterpret_cast<const double2 *>(ba + 256 * a + coff[a & 3]);
+                v[a + 8] = *reinterpret_cast<const double2 *>(bb + 256 * a + coff[a & 3]);
             }
-            // ... whose first 16 see an empty delay line: take out the terms of the raw samples in front of
-            // the window (head table above) and put back the mean term of the dropped coefficients
-            const unsigned char *hp = qs + G::blk_bytes * w; // w = 0: carried over from the previous pass
+        }
+        // ... whose first 16 see an empty delay line: take out the terms of the raw samples in front of
+        // the window (head table above) and put back the mean term of the dropped coefficients. Hop 1's
+        // window starts at r[pre]; hop 0's one block earlier, at r'[blk + pre] of the previous pass.
+        {
+            const unsigned char *hp = hw ? rcur : raw + ((q & 1) ^ 1) * G::raw_bytes + G::blk_bytes;
             const double *trow = tab + lane16 * G::row;
             double X[G::taps];
 #pragma unroll
@@ -425,33 +442,30 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
             }
             const double h = fma(Bm, trow[G::taps], -(A * corr));
             const int s0 = DUP ? lane16 : 2 * lane16, s1 = DUP ? lane16 + 8 : 2 * lane16 + 1;
-            const double h0 = __shfl_sync(0xffffffffu, h, s0 & 15, 16);
-            const double h1 = __shfl_sync(0xffffffffu, h, s1 & 15, 16);
+            const double h0 = __shfl_sync(full, h, s0 & 15, 16);
+            const double h1 = __shfl_sync(full, h, s1 & 15, 16);
             if (lane16 < 8) { v[0].x += h0; v[0].y += h1; }
         }
-        __syncthreads(); // ring blocks and raw samples are consumed
-        if (tid == 0) {
-            // the `pre` raw samples in front of the next tile's first window, then the next tile
-            const int4 *cs = reinterpret_cast<const int4 *>(qs + G::blk_bytes + 15 * G::blk_bytes);
-            int4 *cd = reinterpret_cast<int4 *>(qs);
-            cd[0] = cs[0];
-            if (!DUP) cd[1] = cs[1];
-            if (t + 1 < n_tiles) issue_pass(t + 1);
+        __syncwarp(full); // FIR blocks and raw samples are consumed
+        if (hw == 1) { // block B + 2 (this half-warp's second block) becomes the next pair's block B
+#pragma unroll
+            for (int a = 0; a < 8; ++a) *reinterpret_cast<double2 *>(carry + 256 * a + coff[a & 3]) = v[a + 8];
         }
+        if (lane == 0 && q + 1 < n_pairs) issue_pass(q + 1);
 
-        // ---- 16 x (512-point double real FFT + float-accumulated power), one hop per half-warp;
-        // both half-warps of a warp run in lockstep (an idle one works on stale data and is ignored)
-        if ((w & ~1) < h_cnt) {
-            const unsigned full = 0xffffffffu;
-            double2 *xchg = xchg_all + w * kXchgElems;
+        // ---- 2 x (512-point double real FFT + float-accumulated power), one hop per half-warp in
+        // lockstep (a half-warp without a hop works on stale data and is ignored)
+        {
+            const int hop = B0 + 2 * q + hw;
+            const bool active = 2 * q + hw < n_mine;
             fft256_halfwarp<double>(v, lane16, xchg, p.tw1, full);
             __syncwarp(full);
 #pragma unroll
             for (int r = 0; r < 16; ++r) xchg[lane16 + 16 * fft16_out_index(r)] = v[r];
             __syncwarp(full);
-            double2 B[8]; // Z[256 - k] for this lane's bins k = lane16 + 16 d
+            double2 Bz[8]; // Z[256 - k] for this lane's bins k = lane16 + 16 d
 #pragma unroll
-            for (int d = 0; d < 8; ++d) B[d] = xchg[(256 - (lane16 + 16 * d)) & 255];
+            for (int d = 0; d < 8; ++d) Bz[d] = xchg[(256 - (lane16 + 16 * d)) & 255];
             __syncwarp(full);
             double *xr = reinterpret_cast<double *>(xchg); // |X_k|^2, k = 0..256, at pbin(k)
 #pragma unroll
@@ -464,8 +478,8 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                     xr[pbin(256)] = xn * xn;
                 } else {
                     const double2 wk = p.tw2[k];
-                    const double sr = Zk.x + B[d].x, si = Zk.y - B[d].y;
-                    const double dr = Zk.x - B[d].x, di = Zk.y + B[d].y;
+                    const double sr = Zk.x + Bz[d].x, si = Zk.y - Bz[d].y;
+                    const double dr = Zk.x - Bz[d].x, di = Zk.y + Bz[d].y;
                     const double tr = dr * wk.x - di * wk.y;
                     const double ti = dr * wk.y + di * wk.x;
                     const double ar = sr + ti, ai = si - tr;
@@ -479,10 +493,10 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                 xr[pbin(128)] = Zk.x * Zk.x + Zk.y * Zk.y;
             }
             __syncwarp(full);
-            const double e = float_chain_scan(xr, lane16, w < h_cnt);
-            if (w < h_cnt && lane16 == 0) p.energy[sd.env_off + m0 + w] = e;
+            const double e = float_chain_scan(xr, lane16, active);
+            if (active && lane16 == 0) p.energy[sd.env_off + hop] = e;
         }
-        // no barrier here: the next pass only writes ring blocks and raw samples every thread is done with
+        __syncwarp(full); // the exchange buffers are free for the next pair's FIR blocks
     }
 }
 
@@ -496,8 +510,7 @@ cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, 
         configured = true;
     }
     if (max_hops <= 0) return cudaSuccess;
-    const int per_cta = kEnvH * kTilesPerCta;
-    dim3 grid((unsigned)((max_hops + per_cta - 1) / per_cta), (unsigned)n_songs);
+    dim3 grid((unsigned)((max_hops + kHopsPerCta - 1) / kHopsPerCta), (unsigned)n_songs);
     if (p.dup) envelope_kernel<true><<<grid, kEnvThreads, EG<true>::bytes, st>>>(p);
     else envelope_kernel<false><<<grid, kEnvThreads, EG<false>::bytes, st>>>(p);
     return cudaGetLastError();
