@@ -198,43 +198,145 @@ __device__ __forceinline__ void chain_round(const double *xr, const double (&pv)
     }
 }
 
-__device__ __forceinline__ double float_chain_scan(const double *xr, int lane16, bool active) {
+// Slow path of the accumulation (rare, see float_chain): the binade-by-binade scan from bin 17 on,
+// r16 = the sum after bin 16. Called by all 32 lanes.
+__device__ __noinline__ double float_chain_rounds(const double *xr, int lane16, bool active, double r16) {
     const unsigned full = 0xffffffffu;
     const int lane_base = (threadIdx.x & 16);
     double pv[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) pv[i] = xr[17 * lane16 + 1 + i]; // bins 16 lane16 + 1 + i
-    double r = 0.0;
-    if (active) { // bins 0..16 one by one (the sum climbs through several binades here)
-        float sf = 0.0f;
-#pragma unroll
-        for (int k = 0; k <= 16; ++k) sf = (float)((double)sf + xr[k]);
-        r = (double)sf;
-    }
-    // Largest remaining bin (by its high word, enough for an exponent test): if it is below 2^25 grid
-    // units of the sum after bin 16 it stays so in every later binade: no overflow guard in the rounds.
-    int hmax = 0;
-    if (lane16 != 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) hmax = max(hmax, __double2hiint(pv[i]));
-    }
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) hmax = max(hmax, __shfl_xor_sync(full, hmax, o, 16));
-    const bool guard = active && ((hmax >> 20) > ((__double2hiint(r) >> 20) & 0x7ff) + 1);
+    double r = r16;
     int kdone = 16; // bins 0..kdone are in r
     bool done = !active;
-    if (__any_sync(full, guard)) {
-        while (__any_sync(full, !done)) chain_round<true>(xr, pv, lane16, lane_base, r, kdone, done);
-    } else {
-        while (__any_sync(full, !done)) chain_round<false>(xr, pv, lane16, lane_base, r, kdone, done);
-    }
+    while (__any_sync(full, !done)) chain_round<true>(xr, pv, lane16, lane_base, r, kdone, done);
     return r;
 }
 
-// Ring cell (16 bytes = two consecutive FIR outputs) c of a block, XOR-swizzled so that both the FIR
-// stores (a thread owns 8 consecutive cells) and the FFT loads (a half-warp reads 16 consecutive
-// cells) are bank-conflict free.
-__device__ __forceinline__ int cswz(int cell) { return cell ^ ((cell >> 3) & 7); }
+// Byte offsets of the per-hop scratch behind the 272 doubles of the power spectrum (the hop's FFT exchange
+// buffer is 4352 bytes): integer prefix in front of every bin of lanes' bins j = 16 b + i (vector v of lane b at
+// 16 (16 v + b)), its total, the predicted exponent at the end, the predicted exponent (top 16 bits of the
+// running double sum) in front of every bin, and each lane's mask of binade-crossing bins.
+constexpr int kAuxPb = 0, kAuxTot = 1024, kAuxEnd = 1028, kAuxEg = 1040, kAuxMask = 1552;
+static_assert(272 * 8 + kAuxMask + 32 <= kXchgElems * 16, "scratch fits behind the spectrum");
+
+// sum_fft of reference src/tempo_atk_sort.c:142-150 for the two hops of a warp, one per half-warp:
+// s <- (float)((double)s + p_k), k = 0..256, with p_k = xr[pbin(k)]. `active` is false for a half-warp
+// without a hop. Returns (double)sum_fft on every lane of the half-warp.
+//
+// While s stays inside one binade [2^e, 2^(e+1)) its float grid is g = 2^(e-23) and RN_g(s + p) =
+// s + RN_g(p), so with q = s / g the chain is the integer sum q += I_k, I_k = RN_g(p_k) / g, which one
+// double addition p_k + 1.5 * 2^52 * g leaves in the low mantissa word. Which binade s is in when bin k
+// is added is PREDICTED from the exact prefix sum S_(k-1) of the p_k in double (the float chain stays
+// within 257 * 2^-25 relative of it): lane b owns bins 16 b + 1 .. 16 b + 16, a double prefix scan over the
+// half-warp gives S, every bin is converted ONCE at its predicted grid, and the bins at which the
+// predicted binade changes ("crossings", ~4 per hop) are added one after the other with the reference's
+// own double-add / float-convert step, the integer sums of the bins between them coming from an
+// integer prefix scan. Bins 0..16 (lane 0), where the sum climbs a binade per bin, run as the plain
+// chain meanwhile. Every prediction is VERIFIED on the way (the grid assumed for a run of bins is the
+// grid the chain really has; the sum stays below 2^24 grid units up to the next crossing); a hop that
+// fails (~6e-5 of random spectra: a prefix sum within rounding noise of a power of two) is redone by the
+// binade-by-binade scan above. Host model and test against the sequential chain: tools/chain_model.c.
+__device__ __forceinline__ double float_chain(double *xr, int lane16, bool active) {
+    const unsigned full = 0xffffffffu;
+    unsigned char *aux = reinterpret_cast<unsigned char *>(xr + 272);
+    double pv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pv[i] = xr[17 * lane16 + 1 + i]; // bins 16 lane16 + 1 + i
+    // bins 0..16 one by one (independent of everything up to the resolution below)
+    double r16;
+    {
+        float sf = 0.0f;
+#pragma unroll
+        for (int k = 0; k <= 16; ++k) sf = (float)((double)sf + xr[k]);
+        r16 = (double)sf;
+    }
+    // exact prefix sums in double: local, then across the half-warp
+    double c[16];
+    c[0] = pv[0] + (lane16 == 0 ? xr[0] : 0.0);
+#pragma unroll
+    for (int i = 1; i < 16; ++i) c[i] = c[i - 1] + pv[i];
+    double inc = c[15];
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const double up = __shfl_up_sync(full, inc, o, 16);
+        if (lane16 >= o) inc += up;
+    }
+    double excl = __shfl_up_sync(full, inc, 1, 16);
+    if (lane16 == 0) excl = 0.0;
+    // every bin at its predicted grid; crossing bins and lane 0's bins (already in r16) count nothing
+    const bool mine = active && lane16 != 0;
+    int hprev = __double2hiint(excl);
+    unsigned acc = 0, mask = 0;
+    unsigned L[16], egw[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int hs = __double2hiint(excl + c[i]);
+        const int hiM = (hprev & 0x7FF00000) + 0x1D80000; // 1.5 * 2^(e + 29): ulp = float grid of binade e
+        const double t = pv[i] + __hiloint2double(hiM, 0);
+        const bool x = ((hs ^ hprev) & 0x7FF00000) != 0;
+        L[i] = acc;
+        acc += (x || !mine) ? 0u : (unsigned)__double2loint(t);
+        mask |= x ? (1u << i) : 0u;
+        if (i & 1) egw[i >> 1] = __byte_perm(egw[i >> 1], (unsigned)hprev, 0x7610); // high half <- top 16 bits
+        else egw[i >> 1] = (unsigned)hprev >> 16;
+        hprev = hs;
+    }
+    if (!mine) mask = 0;
+    unsigned incI = acc;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const unsigned up = __shfl_up_sync(full, incI, o, 16);
+        if (lane16 >= o) incI += up;
+    }
+    const unsigned baseI = incI - acc;
+#pragma unroll
+    for (int v4 = 0; v4 < 4; ++v4)
+        *reinterpret_cast<uint4 *>(aux + kAuxPb + 16 * (16 * v4 + lane16)) =
+            make_uint4(baseI + L[4 * v4], baseI + L[4 * v4 + 1], baseI + L[4 * v4 + 2], baseI + L[4 * v4 + 3]);
+#pragma unroll
+    for (int v4 = 0; v4 < 2; ++v4)
+        *reinterpret_cast<uint4 *>(aux + kAuxEg + 16 * (16 * v4 + lane16)) =
+            make_uint4(egw[4 * v4], egw[4 * v4 + 1], egw[4 * v4 + 2], egw[4 * v4 + 3]);
+    *reinterpret_cast<unsigned short *>(aux + kAuxMask + 2 * lane16) = (unsigned short)mask;
+    if (lane16 == 15) {
+        *reinterpret_cast<unsigned *>(aux + kAuxTot) = incI;
+        *reinterpret_cast<int *>(aux + kAuxEnd) = hprev >> 20;
+    }
+    __syncwarp(full);
+    // the crossings in order (no warp-wide operation in here: the two half-warps run their own count)
+    int ex = (__double2hiint(r16) >> 20) & 0x7ff;
+    unsigned q = (((unsigned)__double2hiint(r16) & 0xFFFFFu) << 3) | ((unsigned)__double2loint(r16) >> 29) | 0x800000u;
+    bool ok = !active || (ex >= 1023 - 126 && ex <= 1023 + 126);
+    unsigned Pprev = 0;
+    const uint4 m0 = *reinterpret_cast<const uint4 *>(aux + kAuxMask), m1 = *reinterpret_cast<const uint4 *>(aux + kAuxMask + 16);
+    const unsigned words[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        unsigned m = words[w];
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int b = 2 * w + (bit >> 4), i = bit & 15;
+            const unsigned Pbj = *reinterpret_cast<const unsigned *>(aux + kAuxPb + 16 * (16 * (i >> 2) + b) + 4 * (i & 3));
+            const unsigned eg16 = *reinterpret_cast<const unsigned short *>(aux + kAuxEg + 16 * (16 * (i >> 3) + b) + 2 * (i & 7));
+            const double pk = xr[17 * b + i + 1];
+            const unsigned qb = q + (Pbj - Pprev);
+            ok = ok && qb < (1u << 24) && (int)(eg16 >> 4) == ex;
+            const double sq = __hiloint2double((ex << 20) | (int)((qb & 0x7FFFFFu) >> 3), (int)((qb & 7u) << 29));
+            const double r = (double)(float)(sq + pk); // reference src/tempo_atk_sort.c:147
+            ex = (__double2hiint(r) >> 20) & 0x7ff;
+            q = (((unsigned)__double2hiint(r) & 0xFFFFFu) << 3) | ((unsigned)__double2loint(r) >> 29) | 0x800000u;
+            Pprev = Pbj;
+        }
+    }
+    const unsigned qf = q + (*reinterpret_cast<const unsigned *>(aux + kAuxTot) - Pprev);
+    ok = ok && (!active || (qf < (1u << 24) && *reinterpret_cast<const int *>(aux + kAuxEnd) == ex && ex <= 1023 + 126));
+    double r = __hiloint2double((ex << 20) | (int)((qf & 0x7FFFFFu) >> 3), (int)((qf & 7u) << 29));
+    if (__any_sync(full, !ok)) r = float_chain_rounds(xr, lane16, active, r16);
+    return r;
+}
+
 } // namespace
 
 template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams p) {
@@ -493,7 +595,7 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                 xr[pbin(128)] = Zk.x * Zk.x + Zk.y * Zk.y;
             }
             __syncwarp(full);
-            const double e = float_chain_scan(xr, lane16, active);
+            const double e = float_chain(xr, lane16, active);
             if (active && lane16 == 0) p.energy[sd.env_off + hop] = e;
         }
         __syncwarp(full); // the exchange buffers are free for the next pair's FIR blocks
