@@ -429,8 +429,10 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
     // x = (s / 32768 - mean_d) / var_d (reference src/tempo_atk_sort.c:110-113) is affine in the raw
     // sample s, and the FIR is linear: y = A * (sum c_k s_k) - Bm * (sum c_k), A = 1 / (32768 var_d),
     // Bm = mean_d / var_d. The taps run over exact integers; one FMA per output normalises.
-    const double A = nm.inv_var_d * (1.0 / 32768);
-    const double Bm = nm.mean_d * nm.inv_var_d;
+    // Both carry an extra factor 1/2 (exact): it is the 1/2 of the real-FFT even/odd split, so the split
+    // below produces X_k without its 0.25 |.|^2 scaling step; the three purely real bins are scaled back.
+    const double A = nm.inv_var_d * (1.0 / 32768) * 0.5;
+    const double Bm = nm.mean_d * nm.inv_var_d * 0.5;
     double csum_all = fir_tap(8);
 #pragma unroll
     for (int k = 0; k < 8; ++k) csum_all += 2.0 * fir_tap(k);
@@ -563,7 +565,8 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
             fft256_halfwarp<double>(v, lane16, xchg, p.tw1, full);
             __syncwarp(full);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) xchg[lane16 + 16 * fft16_out_index(r)] = v[r];
+            for (int r = 0; r < 16; ++r) // only Z[129..255] are read back below
+                if (fft16_out_index(r) >= 8) xchg[lane16 + 16 * fft16_out_index(r)] = v[r];
             __syncwarp(full);
             double2 Bz[8]; // Z[256 - k] for this lane's bins k = lane16 + 16 d
 #pragma unroll
@@ -576,8 +579,8 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                 const double2 Zk = v[fft16_reg_of(d)];
                 if (k == 0) {
                     const double x0 = Zk.x + Zk.y, xn = Zk.x - Zk.y; // X_0 and X_256 are real
-                    xr[pbin(0)] = x0 * x0;
-                    xr[pbin(256)] = xn * xn;
+                    xr[pbin(0)] = 4.0 * (x0 * x0);
+                    xr[pbin(256)] = 4.0 * (xn * xn);
                 } else {
                     const double2 wk = p.tw2[k];
                     const double sr = Zk.x + Bz[d].x, si = Zk.y - Bz[d].y;
@@ -586,13 +589,13 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                     const double ti = dr * wk.y + di * wk.x;
                     const double ar = sr + ti, ai = si - tr;
                     const double cr = sr - ti, ci = si + tr;
-                    xr[pbin(k)] = 0.25 * (ar * ar + ai * ai);
-                    xr[pbin(256 - k)] = 0.25 * (cr * cr + ci * ci);
+                    xr[pbin(k)] = ar * ar + ai * ai;
+                    xr[pbin(256 - k)] = cr * cr + ci * ci;
                 }
             }
             if (lane16 == 0) {
                 const double2 Zk = v[fft16_reg_of(8)];
-                xr[pbin(128)] = Zk.x * Zk.x + Zk.y * Zk.y;
+                xr[pbin(128)] = 4.0 * (Zk.x * Zk.x + Zk.y * Zk.y);
             }
             __syncwarp(full);
             const double e = float_chain(xr, lane16, active);
