@@ -271,6 +271,7 @@ struct ChunkPlan {
     int max_hops = 0;
     long long energy_total = 0;
     long long q_total = 0;
+    long long pcm_rows = 0; // float32 input: rows of 64 floats the packed buffer is readable for
 };
 
 // Fills n descriptors. offsets/lengths are in input elements.
@@ -295,6 +296,7 @@ static void plan_songs(int fmt, const long long *offsets, const long long *lengt
             d.duration = (unsigned)(lengths[i] / BLX_FE_IN_RATE);
             d.q_off = q;
             q += round_up(std::max(d.n_msamples, 1), 64);
+            plan->pcm_rows = std::max(plan->pcm_rows, (offsets[i] + round_up(std::max(lengths[i], 1ll), BLX_ALIGN_ELEMS)) / 64);
         } else {
             d.n_samples = (int)lengths[i];
             d.n_msamples = (plan->kind == kInS16Mono) ? d.n_samples : d.n_samples / 2;
@@ -374,6 +376,9 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         p.hist = static_cast<unsigned *>(s.hist.p);
         p.stats = static_cast<SongStats *>(s.stats.p);
         p.qout = static_cast<short *>(s.q.p);
+        memset(&p.map_a, 0, sizeof(p.map_a));
+        memset(&p.map_b, 0, sizeof(p.map_b));
+        if (plan.kind == kInF32) CK(make_pass1_maps(&p, d_pcm, plan.pcm_rows));
         ProfScope ps(e, BLX_K_PASS1, st);
         CK(launch_pass1(plan.kind, full, p, plan.max_parts, n, st));
     }

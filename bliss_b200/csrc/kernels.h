@@ -1,5 +1,6 @@
 // kernels.h — launch interfaces between the engine (engine.cu) and the kernel translation units.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "blx_common.cuh"
 
@@ -15,7 +16,12 @@ struct Pass1Params {
     unsigned *hist;         // [n_songs][kHistStride]   (FULL)
     SongStats *stats;       // [n_songs]                (FULL)
     short *qout;            // decimated int16 stream   (FULL, F32 input)
+    // F32 input: the packed buffer as rows of 64 floats, first / second 128 bytes of every row
+    // (2-D tensor maps {32 floats, rows}, row stride 256 bytes, box {32, 129}, 128-byte swizzle)
+    CUtensorMap map_a, map_b;
 };
+// Fills map_a / map_b for a float32 buffer of `rows` rows of 64 floats at d_pcm (16-byte aligned).
+cudaError_t make_pass1_maps(Pass1Params *p, const void *d_pcm, long long rows);
 cudaError_t launch_pass1(int kind, bool full, const Pass1Params &p, int max_parts, int n_songs, cudaStream_t st);
 int pass1_tile_msamples();
 

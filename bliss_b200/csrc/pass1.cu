@@ -3,10 +3,14 @@
 // One launch covers a batch of songs. A CTA (128 threads) owns one (song, part) pair and walks
 // tiles of 8 frames (4096 per-channel samples) of that song:
 //
-//   1. TMA: every thread issues one 1-D bulk copy (cp.async.bulk, SASS UBLKCP) of its 32-sample row
-//      into a padded shared-memory row (row stride = row bytes + 16, so that the 128-bit reads of the
-//      next step are bank-conflict free); completion is tracked by one mbarrier per CTA. The copy for
-//      the next tile is issued as soon as the rows are consumed, so it overlaps the FFTs.
+//   1. TMA. Float32 input (the benchmark path): the packed PCM buffer is described by two 2-D tensor maps
+//      over rows of 64 floats (256 bytes, one row per thread) - the first 128 bytes of every row and the
+//      second 128 bytes - and ONE elected thread issues two tensor copies per tile (cp.async.bulk.tensor,
+//      SASS UTMALDG), 129 rows each (the tile's 128 rows plus the half row of FIR history / look-ahead on
+//      either side), with the 128-byte swizzle, so that the per-thread 128-bit reads of the next step are
+//      bank-conflict free without padding. int16 input: every thread issues one 1-D bulk copy (UBLKCP) of
+//      its row into a padded shared row. Completion is tracked by one mbarrier per CTA; the copy for the
+//      next tile is issued as soon as the rows are consumed, so it overlaps the FFTs.
 //   2. Per row: front-end (F32 input: 23-tap half-band 2:1 decimation + int16 quantisation, bit-exact
 //      with blx_frontend.h) or stereo down-mix (S16 input: (L + R) / 2, C truncation, reference
 //      src/frequency_sort.c:71-74), times the Hann window (reference src/frequency_sort.c:40-42,74),
@@ -45,7 +49,11 @@ template <int KIND> struct P1Smem {
     static constexpr int row_bytes = G::elems * G::ebytes;
     static constexpr int row_stride = row_bytes + 16;
     static constexpr int n_slots = kP1Threads + 2 * G::halo;
-    static constexpr int raw_bytes = n_slots * row_stride;
+    // F32: region A = first halves of rows 0..128 (129 x 128 bytes), region B = second halves of rows -1..127,
+    // both written by tensor copies with the 128-byte swizzle; B starts on a 1024-byte boundary.
+    static constexpr int f32_half = 128, f32_rows = kP1Threads + 1;
+    static constexpr int off_a = 0, off_b = 17 * 1024;
+    static constexpr int raw_bytes = (KIND == kInF32) ? off_b + f32_rows * f32_half : n_slots * row_stride;
     static constexpr int off_raw = 0;
     static constexpr int off_fin = (raw_bytes + 127) / 128 * 128;
     static constexpr int fin_bytes = kP1FramesPerTile * kFinFrame * 4; // 18432; also 8 KB reduction scratch
@@ -57,6 +65,20 @@ template <int KIND> struct P1Smem {
     static constexpr int bytes_lite = off_hist;
     static constexpr int bytes_full = off_hist + kHistStride * 4;
 };
+
+// 2-D tensor copy global -> shared (SASS: UTMALDG), completion on an mbarrier. c0 = element, c1 = row.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Address of 16-byte chunk c of the 128-byte row at `row` inside a swizzled region (row is 128-byte aligned):
+// the copy engine XORs the chunk index with bits 7..9 of the shared-memory address.
+__device__ __forceinline__ const float4 *swz_chunk(const unsigned char *row, unsigned key16, int c) {
+    return reinterpret_cast<const float4 *>(row + (((unsigned)c << 4) ^ key16));
+}
+__device__ __forceinline__ unsigned swz_key16(const void *row) { return ((smem_u32(row) >> 7) & 7u) << 4; }
 
 // Histogram of sample values -1904..+1902 (the only bins that can reach the integral of reference
 // src/amplitude_sort.c:69-71): one predicated shared-memory atomic per sample.
@@ -73,7 +95,7 @@ struct ThreadStats {
 } // namespace
 
 template <int KIND, bool FULL>
-__global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
+__global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant__ Pass1Params p) {
     using SM = P1Smem<KIND>;
     using G = RowGeom<KIND>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -114,6 +136,17 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
     auto issue_tile = [&](int tile) {
         const long long e0 = (long long)tile * kP1Threads * G::elems;
         fence_proxy_async();
+        if (KIND == kInF32) {
+            // rows of 64 floats; the tile's rows 0..128 (first halves) and -1..127 (second halves). Rows outside
+            // the buffer arrive as zeros, rows of a neighbouring song are cleared by the fix-up below.
+            if (tid == 0) {
+                const int row0 = (int)(sd.pcm_off >> 6) + tile * kP1Threads;
+                mbar_arrive_expect_tx(bar, 2u * SM::f32_rows * SM::f32_half);
+                tma_load_2d(raw + SM::off_a, &p.map_a, 0, row0, bar);
+                tma_load_2d(raw + SM::off_b, &p.map_b, 0, row0 - 1, bar);
+            }
+            return;
+        }
         if (tid == 0) {
             long long first = e0 - (long long)G::halo * G::elems;
             if (first < 0) first = 0;
@@ -127,12 +160,6 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
             const long long es = e0 + (long long)tid * G::elems;
             if (es < n_elems)
                 tma_load_1d(raw + (size_t)(tid + G::halo) * SM::row_stride, src + es * G::ebytes, SM::row_bytes, bar);
-        }
-        if (G::halo && tid < 2) {
-            const long long es = (tid == 0) ? e0 - G::elems : e0 + (long long)kP1Threads * G::elems;
-            const int slot = (tid == 0) ? 0 : kP1Threads + 1;
-            if (es >= 0 && es < n_elems)
-                tma_load_1d(raw + (size_t)slot * SM::row_stride, src + es * G::ebytes, SM::row_bytes, bar);
         }
     };
 
@@ -159,16 +186,24 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
         if (edge) {
             for (int slot = tid; slot < SM::n_slots; slot += kP1Threads) {
                 const long long es = e0 + (long long)(slot - G::halo) * G::elems;
+                if (KIND == kInF32) {
+                    // row s = slot - 1: elements 0..31 in region A row s (s >= 0), 32..63 in region B row s + 1 (s <= 127)
+                    const int s = slot - 1;
+                    const int keep = (es < 0 || es >= n_elems) ? 0 : (int)min((long long)G::elems, n_elems - es);
+                    for (int el = keep; el < G::elems; ++el) {
+                        const int half = el >> 5;
+                        if ((half == 0 && s < 0) || (half == 1 && s > kP1Threads - 1)) continue;
+                        unsigned char *row = raw + (half ? SM::off_b + (s + 1) * SM::f32_half : SM::off_a + s * SM::f32_half);
+                        *reinterpret_cast<float *>(row + ((((unsigned)(el & 31) >> 2) << 4) ^ swz_key16(row)) + 4 * (el & 3)) = 0.0f;
+                    }
+                    continue;
+                }
                 unsigned char *row = raw + (size_t)slot * SM::row_stride;
                 if (es < 0 || es >= n_elems) {
                     for (int i = 0; i < SM::row_bytes / 16; ++i) reinterpret_cast<int4 *>(row)[i] = make_int4(0, 0, 0, 0);
                 } else if (es + G::elems > n_elems) {
                     const int keep = (int)(n_elems - es);
-                    if (G::ebytes == 4) {
-                        for (int i = keep; i < G::elems; ++i) reinterpret_cast<float *>(row)[i] = 0.0f;
-                    } else {
-                        for (int i = keep; i < G::elems; ++i) reinterpret_cast<short *>(row)[i] = 0;
-                    }
+                    for (int i = keep; i < G::elems; ++i) reinterpret_cast<short *>(row)[i] = 0;
                 }
             }
             __syncthreads();
@@ -181,14 +216,17 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
 
         if (KIND == kInF32) {
             const float H[BLX_FE_NPAIRS] = BLX_FE_TAPS;
-            const float4 *rowp = reinterpret_cast<const float4 *>(raw + (size_t)(tid + 1) * SM::row_stride);
-            const float4 *prevp = reinterpret_cast<const float4 *>(raw + (size_t)tid * SM::row_stride);
-            const float4 *nextp = reinterpret_cast<const float4 *>(raw + (size_t)(tid + 2) * SM::row_stride);
+            // chunk c (16 bytes) of this thread's row: 0..7 in region A row tid, 8..15 in region B row tid + 1;
+            // the previous row's chunks 13..15 are region B row tid, the next row's chunks 0..2 region A row tid + 1
+            const unsigned char *ra = raw + SM::off_a + tid * SM::f32_half, *rb = raw + SM::off_b + tid * SM::f32_half;
+            const unsigned ka = swz_key16(ra), ka1 = swz_key16(ra + SM::f32_half);
+            const unsigned kb = swz_key16(rb), kb1 = swz_key16(rb + SM::f32_half);
+            auto own = [&](int c) -> float4 { return c < 8 ? *swz_chunk(ra, ka, c) : *swz_chunk(rb + SM::f32_half, kb1, c - 8); };
             const long long n_out = n_elems >> 1;
             float w[32];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const float4 a = prevp[13 + i], b = rowp[i];
+                const float4 a = *swz_chunk(rb, kb, 5 + i), b = own(i);
                 w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
                 w[12 + 4 * i] = b.x; w[12 + 4 * i + 1] = b.y; w[12 + 4 * i + 2] = b.z; w[12 + 4 * i + 3] = b.w;
             }
@@ -201,7 +239,7 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
                     const int q4 = 2 * s + 3 + h2;
-                    const float4 a = (q4 < 16) ? rowp[q4] : nextp[q4 - 16];
+                    const float4 a = (q4 < 16) ? own(q4) : *swz_chunk(ra + SM::f32_half, ka1, q4 - 16);
                     w[24 + 4 * h2] = a.x; w[25 + 4 * h2] = a.y; w[26 + 4 * h2] = a.z; w[27 + 4 * h2] = a.w;
                 }
                 float o[4];
@@ -397,6 +435,36 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(Pass1Params p) {
             if (c) atomicAdd(&ghist[i], c);
         }
     }
+}
+
+// ---------------------------------------------------------------- tensor maps (float32 input)
+cudaError_t make_pass1_maps(Pass1Params *p, const void *d_pcm, long long rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    if (rows < 1) rows = 1;
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15) || rows > 0x7fffffffll) return cudaErrorInvalidValue;
+    const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {256};
+    const cuuint32_t box[2] = {32, (cuuint32_t)P1Smem<kInF32>::f32_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    unsigned char *base = const_cast<unsigned char *>(static_cast<const unsigned char *>(d_pcm));
+    for (int h = 0; h < 2; ++h) {
+        const CUresult r = encode(h ? &p->map_b : &p->map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base + 128 * h, dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
 }
 
 // ---------------------------------------------------------------- launcher
