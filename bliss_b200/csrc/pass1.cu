@@ -59,8 +59,7 @@ template <int KIND> struct P1Smem {
     static constexpr int fin_bytes = kP1FramesPerTile * kFinFrame * 4; // 18432; also 8 KB reduction scratch
     static constexpr int off_hann = off_fin + fin_bytes;
     static constexpr int off_tw1 = off_hann + kFinFrame * 4;
-    static constexpr int off_tw2 = off_tw1 + 256 * 8;
-    static constexpr int off_bar = off_tw2 + 128 * 8;
+    static constexpr int off_bar = off_tw1 + 256 * 8;
     static constexpr int off_hist = off_bar + 16;
     static constexpr int bytes_lite = off_hist;
     static constexpr int bytes_full = off_hist + kHistStride * 4;
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant
     float *fin = reinterpret_cast<float *>(smem + SM::off_fin);
     float *hannp = reinterpret_cast<float *>(smem + SM::off_hann);
     float2 *tw1 = reinterpret_cast<float2 *>(smem + SM::off_tw1);
-    float2 *tw2 = reinterpret_cast<float2 *>(smem + SM::off_tw2);
+    const float2 *tw2 = p.tw2; // 8 entries per thread and tile: read through L1 (keeps four CTAs per SM in shared memory)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SM::off_bar);
     unsigned *hist = reinterpret_cast<unsigned *>(smem + SM::off_hist);
 
@@ -118,7 +117,6 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant
     // ---- one-time setup: tables into shared memory, histogram cleared, barrier armed
     for (int i = tid; i < kWin; i += kP1Threads) hannp[(i >> 5) * 36 + (i & 31)] = p.hann[i];
     for (int i = tid; i < 256; i += kP1Threads) tw1[i] = p.tw1[i];
-    for (int i = tid; i < 128; i += kP1Threads) tw2[i] = p.tw2[i];
     if (FULL)
         for (int i = tid; i < kHistStride; i += kP1Threads) hist[i] = 0u;
     if (tid == 0) {
@@ -373,7 +371,7 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant
                     if (k != 0) { // bins k and 512/2 - k from Z[k], Z[256 - k]
                         const float2 A = v[fft16_reg_of(d)];
                         const float2 B = xchg[256 - k];
-                        const float2 wk = tw2[k];
+                        const float2 wk = __ldg(tw2 + k);
                         const float sr = A.x + B.x, si = A.y - B.y;
                         const float dr = A.x - B.x, di = A.y + B.y;
                         const float tr = dr * wk.x - di * wk.y;
