@@ -276,11 +276,13 @@ struct ChunkPlan {
 
 // Fills n descriptors. offsets/lengths are in input elements.
 static void plan_songs(int fmt, const long long *offsets, const long long *lengths, int channels_kind,
-                       const unsigned long long *durations, int n, SongDesc *sd, ChunkPlan *plan) {
+                       const unsigned long long *durations, int n, SongDesc *sd, ChunkPlan *plan, bool spectral_only = false) {
     const int tile_m = pass1_tile_msamples();
     // A song is cut into parts of kTilesPerPart consecutive tiles, one CTA each. The cut depends on the
     // song alone, so its partial spectra (and their float summation order) are the same in any batch.
-    const int kTilesPerPart = 64;
+    // (The full pass pays a histogram clear + flush per CTA, hence larger parts; the spectral-only pass has
+    // almost no per-CTA cost and takes small parts so that short songs still fill the 148 SMs evenly.)
+    const int kTilesPerPart = spectral_only ? 16 : 64;
     plan->kind = (fmt == BLX_FMT_F32) ? kInF32 : channels_kind;
     long long env = 0, q = 0;
     int parts = 0;
@@ -464,7 +466,8 @@ static int analyze_device_impl(blx_engine *e, int fmt, const void *d_pcm, const 
         ChunkPlan plan;
         plan_songs(fmt, reinterpret_cast<const long long *>(offsets + i0), reinterpret_cast<const long long *>(lengths + i0),
                    ch0 == 1 ? kInS16Mono : kInS16Stereo,
-                   duration_s ? reinterpret_cast<const unsigned long long *>(duration_s + i0) : nullptr, n, s.h_songs, &plan);
+                   duration_s ? reinterpret_cast<const unsigned long long *>(duration_s + i0) : nullptr, n, s.h_songs, &plan,
+                   d_freq_only != nullptr);
         rc = run_chunk(e, s, plan, d_pcm, n, what, d_out ? d_out + i0 : nullptr, d_freq_only ? d_freq_only + i0 : nullptr, st);
         if (rc) return rc;
         CK(cudaEventRecord(s.done, st));

@@ -285,10 +285,16 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant
                 }
             }
             if (FULL && m0 < n_out) { // decimated stream for the envelope pass (mono: L == R)
-                int4 *dst = reinterpret_cast<int4 *>(p.qout + sd.q_off + m0);
+                // two 256-bit stores (STG.256: a full 32-byte sector per lane); q rows are padded to 32 samples by the engine
+                short *dst = p.qout + sd.q_off + m0;
                 const int4 *srcq = reinterpret_cast<const int4 *>(qv);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = srcq[i]; // q rows are padded to 32 samples by the engine
+                for (int i = 0; i < 2; ++i) {
+                    const int4 a = srcq[2 * i], b = srcq[2 * i + 1];
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * i), "r"(a.x), "r"(a.y),
+                                 "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                                 : "memory");
+                }
             }
         } else {
             const int4 *rowp = reinterpret_cast<const int4 *>(raw + (size_t)tid * SM::row_stride);
