@@ -347,8 +347,11 @@ static int ensure_host_songs(Slot &s, int n) {
 }
 
 // Songs already described in s.h_songs[0..n). d_pcm is the packed input.
+// The descriptors are uploaded here unless the caller already queued that copy (host-buffer path: behind the
+// chunk's PCM on the copy stream - a small host->device copy on the compute stream would wait in the copy
+// engine behind the NEXT chunk's PCM and stall this chunk's kernels for a whole chunk copy).
 static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *d_pcm, int n, unsigned what,
-                     blx_result *d_out, float *d_freq_only, cudaStream_t st) {
+                     blx_result *d_out, float *d_freq_only, cudaStream_t st, bool songs_uploaded = false) {
     const bool full = (d_freq_only == nullptr);
     CK(s.songs.reserve((size_t)n * sizeof(SongDesc)));
     CK(s.partials.reserve((size_t)std::max(plan.parts_total, 1) * 256 * sizeof(float)));
@@ -360,7 +363,7 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         CK(s.xlog.reserve((size_t)(std::max(plan.energy_total, 8ll) + 16) * sizeof(double))); // + read-ahead slack of the tail
         if (plan.kind == kInF32) CK(s.q.reserve((size_t)std::max(plan.q_total, 64ll) * sizeof(short)));
     }
-    CK(cudaMemcpyAsync(s.songs.p, s.h_songs, (size_t)n * sizeof(SongDesc), cudaMemcpyHostToDevice, st));
+    if (!songs_uploaded) CK(cudaMemcpyAsync(s.songs.p, s.h_songs, (size_t)n * sizeof(SongDesc), cudaMemcpyHostToDevice, st));
     if (full) {
         CK(cudaMemsetAsync(s.hist.p, 0, (size_t)n * kHistStride * sizeof(unsigned), st));
         CK(cudaMemsetAsync(s.stats.p, 0, (size_t)n * sizeof(SongStats), st));
@@ -503,6 +506,11 @@ static int analyze_host_impl(blx_engine *e, int fmt, const T *const *pcm, const 
     const size_t cap_elems = e->chunk_bytes / sizeof(T);
     std::vector<long long> offs;
     int i0 = 0;
+    // BLX_TRACE=1: per-chunk timeline (copy start/end, compute start/end, ms since the call started) on stderr
+    const bool trace = getenv("BLX_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); tev.push_back(ev); } };
+    mark(e->copy);
     int pending[2] = {-1, -1}; // first song of the chunk in flight in each slot
     int pending_n[2] = {0, 0};
     auto collect = [&](int si) -> int {
@@ -543,16 +551,22 @@ static int analyze_host_impl(blx_engine *e, int fmt, const T *const *pcm, const 
         rc = ensure_host_songs(s, n);
         if (rc) return rc;
         CK(s.results.reserve((size_t)n * sizeof(blx_result)));
+        mark(e->copy);
         for (int i = 0; i < n; ++i)
             CK(cudaMemcpyAsync(static_cast<T *>(s.pcm.p) + offs[i], pcm[i0 + i], (size_t)lengths[i0 + i] * sizeof(T),
                                cudaMemcpyHostToDevice, e->copy));
-        CK(cudaEventRecord(s.copied, e->copy));
-        CK(cudaStreamWaitEvent(e->compute, s.copied, 0));
+        mark(e->copy);
         ChunkPlan plan;
         plan_songs(fmt, offs.data(), lengths + i0, ch0 == 1 ? kInS16Mono : kInS16Stereo,
                    duration_s ? reinterpret_cast<const unsigned long long *>(duration_s + i0) : nullptr, n, s.h_songs, &plan);
-        rc = run_chunk(e, s, plan, s.pcm.p, n, what, static_cast<blx_result *>(s.results.p), nullptr, e->compute);
+        CK(s.songs.reserve((size_t)n * sizeof(SongDesc)));
+        CK(cudaMemcpyAsync(s.songs.p, s.h_songs, (size_t)n * sizeof(SongDesc), cudaMemcpyHostToDevice, e->copy));
+        CK(cudaEventRecord(s.copied, e->copy));
+        CK(cudaStreamWaitEvent(e->compute, s.copied, 0));
+        mark(e->compute);
+        rc = run_chunk(e, s, plan, s.pcm.p, n, what, static_cast<blx_result *>(s.results.p), nullptr, e->compute, true);
         if (rc) return rc;
+        mark(e->compute);
         CK(cudaMemcpyAsync(s.h_results, s.results.p, (size_t)n * sizeof(blx_result), cudaMemcpyDeviceToHost, e->compute));
         CK(cudaEventRecord(s.done, e->compute));
         s.busy = true;
@@ -563,6 +577,15 @@ static int analyze_host_impl(blx_engine *e, int fmt, const T *const *pcm, const 
     rc = collect(e->next_slot);
     if (rc) return rc;
     rc = collect(e->next_slot ^ 1);
+    if (trace) {
+        cudaDeviceSynchronize();
+        for (size_t k = 1; k + 3 < tev.size() + 1; k += 4) {
+            float t[4];
+            for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[k + j]);
+            fprintf(stderr, "[blx trace] chunk %zu: copy %.2f..%.2f ms, compute %.2f..%.2f ms\n", (k - 1) / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+    }
     return rc;
 }
 

@@ -23,3 +23,13 @@ for chunk in [256 << 20, 512 << 20, 1 << 30, 2 << 30, 4 << 30]:
     dt = (time.perf_counter() - t0) / 2
     print(f"chunk {chunk >> 20} MiB: {Be / dt:.0f} songs/s, {Be * n_in * 4 / dt / 1e9:.1f} GB/s, {dt * 1e3:.1f} ms", flush=True)
     eng.close()
+# pure copy baselines over the same pinned buffer: one 8 GB copy, and song-sized pieces
+dev = torch.empty(64 * stride, dtype=torch.float32, device="cuda")
+for pieces in [1, 64]:
+    n = 64 * stride // pieces
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for rep in range(4):
+        for k in range(pieces):
+            dev[k * n:(k + 1) * n].copy_(pinned[(rep * 64 * stride) + k * n:(rep * 64 * stride) + (k + 1) * n], non_blocking=True)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f"pure H2D, {pieces} pieces per 2 GB: {4 * 64 * stride * 4 / dt / 1e9:.1f} GB/s", flush=True)
