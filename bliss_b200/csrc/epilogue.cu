@@ -314,9 +314,22 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
                 step_steady(d);
                 e3 = e2; e2 = e1; e1 = e0;
             };
-            // read-ahead of four inputs (8 samples, ~1000 cycles) in registers that are never moved, so
-            // a load is only waited for when its value is used (rows carry 16 doubles of slack)
+            // read-ahead of four to eight inputs (8-16 samples, >= 1000 cycles) in two register sets that
+            // take turns, so that no load has to be waited for (or its value moved) before its turn
+            // (rows carry 16 doubles of slack)
             double q0 = X[i], q1 = X[i + 1], q2 = X[i + 2], q3 = X[i + 3];
+            for (; j + 16 <= n2 - 1; j += 16, i += 8) {
+                // every lane streams its own row (one 32-byte sector per 4 inputs, a DRAM page of its own):
+                // pull the sectors of ~50 samples ahead into L1 so that the loads below are L1 hits
+                if (2 * (i + 32) < n2) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(X + i + 28));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(X + i + 32));
+                }
+                const double u0 = X[i + 4], u1 = X[i + 5], u2 = X[i + 6], u3 = X[i + 7];
+                pair(q0); pair(q1); pair(q2); pair(q3);
+                q0 = X[i + 8]; q1 = X[i + 9]; q2 = X[i + 10]; q3 = X[i + 11];
+                pair(u0); pair(u1); pair(u2); pair(u3);
+            }
             for (; j + 8 <= n2 - 1; j += 8, i += 4) {
                 double e0 = q0; q0 = X[i + 4]; pair(e0);
                 e0 = q1; q1 = X[i + 5]; pair(e0);
