@@ -55,7 +55,7 @@ BLISS_H_SYMBOLS = [
     "bl_version", "bl_initialize_song", "bl_mean", "bl_variance", "bl_rectangular_filter",
 ]
 BLX_H_SYMBOLS = [
-    "blx_device_count", "blx_init", "blx_shutdown", "blx_last_error", "blx_configure",
+    "blx_device_count", "blx_init", "blx_shutdown", "blx_last_error", "blx_configure", "blx_debug_flags",
     "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_device", "blx_spectral_device",
     "blx_distance_matrix", "blx_cosine_matrix", "blx_distance_rows_device", "blx_distance_nearest_device",
     "blx_mean_variance_s16", "blx_rectangular_filter", "blx_frontend_f32", "blx_envelope_energy_s16",
@@ -84,6 +84,8 @@ def load():
     L.blx_last_error.restype = ctypes.c_char_p
     L.blx_configure.restype = ctypes.c_int
     L.blx_configure.argtypes = [vp, ctypes.c_size_t]
+    L.blx_debug_flags.restype = ctypes.c_int
+    L.blx_debug_flags.argtypes = [vp, ctypes.c_uint]
     L.blx_analyze_batch_s16.restype = ctypes.c_int
     L.blx_analyze_batch_s16.argtypes = [vp, ctypes.POINTER(vp), c_i32p, c_i32p, c_u64p, ctypes.c_int,
                                         ctypes.c_uint, ctypes.POINTER(BlxResult)]

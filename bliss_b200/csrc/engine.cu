@@ -84,6 +84,7 @@ struct blx_engine {
     Slot slot[2];
     int next_slot = 0;
     size_t chunk_bytes = (size_t)1 << 30;
+    unsigned debug = 0;
     bool prof = false;
     std::vector<ProfRec> prof_pending;
     std::vector<cudaEvent_t> ev_pool;
@@ -261,6 +262,12 @@ extern "C" int blx_configure(blx_engine *e, size_t chunk_bytes) {
     return BLX_OK;
 }
 
+extern "C" int blx_debug_flags(blx_engine *e, unsigned flags) {
+    if (!e) return fail(BLX_ERR_ARG, "null engine");
+    e->debug = flags;
+    return BLX_OK;
+}
+
 // ---------------------------------------------------------------- descriptors
 static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
@@ -409,6 +416,7 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         p.tw2 = e->d_tw2d;
         p.energy = static_cast<double *>(s.energy.p);
         p.dup = (plan.kind == kInF32) ? 1 : 0;
+        p.slow_chain = (e->debug & BLX_DEBUG_SLOW_CHAIN) ? 1 : 0;
         ProfScope ps(e, BLX_K_ENVELOPE, st);
         CK(launch_envelope(p, plan.max_hops, n, st));
     }

@@ -237,7 +237,7 @@ static_assert(272 * 8 + kAuxMask + 32 <= kXchgElems * 16, "scratch fits behind t
 // grid the chain really has; the sum stays below 2^24 grid units up to the next crossing); a hop that
 // fails (~6e-5 of random spectra: a prefix sum within rounding noise of a power of two) is redone by the
 // binade-by-binade scan above. Host model and test against the sequential chain: tools/chain_model.c.
-__device__ __forceinline__ double float_chain(double *xr, int lane16, bool active) {
+__device__ __forceinline__ double float_chain(double *xr, int lane16, bool active, bool force_slow) {
     const unsigned full = 0xffffffffu;
     unsigned char *aux = reinterpret_cast<unsigned char *>(xr + 272);
     double pv[16];
@@ -333,7 +333,7 @@ __device__ __forceinline__ double float_chain(double *xr, int lane16, bool activ
     const unsigned qf = q + (*reinterpret_cast<const unsigned *>(aux + kAuxTot) - Pprev);
     ok = ok && (!active || (qf < (1u << 24) && *reinterpret_cast<const int *>(aux + kAuxEnd) == ex && ex <= 1023 + 126));
     double r = __hiloint2double((ex << 20) | (int)((qf & 0x7FFFFFu) >> 3), (int)((qf & 7u) << 29));
-    if (__any_sync(full, !ok)) r = float_chain_rounds(xr, lane16, active, r16);
+    if (__any_sync(full, !ok) || force_slow) r = float_chain_rounds(xr, lane16, active, r16);
     return r;
 }
 
@@ -598,7 +598,7 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                 xr[pbin(128)] = 4.0 * (Zk.x * Zk.x + Zk.y * Zk.y);
             }
             __syncwarp(full);
-            const double e = float_chain(xr, lane16, active);
+            const double e = float_chain(xr, lane16, active, p.slow_chain != 0);
             if (active && lane16 == 0) p.energy[sd.env_off + hop] = e;
         }
         __syncwarp(full); // the exchange buffers are free for the next pair's FIR blocks

@@ -44,6 +44,7 @@ struct EnvelopeParams {
     const double2 *tw2;      // [128]
     double *energy;          // rows of 2F doubles at SongDesc::env_off: E[m]
     int dup;                 // 1: logical S[i] = stream[q_off + (i >> 1)]; 0: S[i] = stream[pcm_off + i]
+    int slow_chain;          // test hook (BLX_DEBUG_SLOW_CHAIN): every hop takes the fallback accumulation path
 };
 cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, cudaStream_t st);
 

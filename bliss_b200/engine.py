@@ -14,6 +14,7 @@ FMT_S16, FMT_F32 = 0, 1
 ALIGN_ELEMS = 64
 K_PASS1, K_EPILOGUE, K_ENVELOPE, K_TAIL, K_DISTANCE, K_COUNT = 0, 1, 2, 3, 4, 5
 SONG_TOO_SHORT, SONG_SILENT, SONG_FLAT = 0x1, 0x2, 0x4
+DEBUG_SLOW_CHAIN = 0x1
 
 RESULT_DTYPE = np.dtype([("tempo", "<f4"), ("amplitude", "<f4"), ("frequency", "<f4"), ("attack", "<f4"),
                          ("force", "<f4"), ("calm_or_loud", "<i4"), ("beat", "<i4"), ("status", "<i4")])
@@ -161,6 +162,10 @@ class Engine:
         E = np.zeros(max(nb, 1), dtype=np.float64)
         self._ck(self._lib.blx_envelope_energy_s16(self._h, a.ctypes.data_as(L.c_i16p), len(a), E.ctypes.data_as(L.c_f64p)))
         return E[:nb]
+
+    def debug_flags(self, flags):
+        """Test hooks (include/blx.h BLX_DEBUG_*); results must not depend on them."""
+        self._ck(self._lib.blx_debug_flags(self._h, int(flags)))
 
     # ------------------------------------------------------------------ measurement
     def profile(self, on=True):

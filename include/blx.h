@@ -74,6 +74,11 @@ const char *blx_last_error(void);
  * two device staging buffers used by the host-buffer entry points (default 1 GiB). */
 int blx_configure(blx_engine *e, size_t chunk_bytes);
 
+/* Test hooks (results must not depend on them). BLX_DEBUG_SLOW_CHAIN: the envelope kernel takes
+ * its fallback path (binade-by-binade scan) for the float accumulation of every hop. */
+#define BLX_DEBUG_SLOW_CHAIN 1u
+int blx_debug_flags(blx_engine *e, unsigned flags);
+
 /* ---- per-song analysis, HOST buffers (the end-to-end path) -------------------
  * Replaces the analysis part of bl_analyze (reference src/analyze.c:43-79) for a
  * batch of songs already decoded in host memory. Copies are chunked and

@@ -269,3 +269,69 @@ def test_long_song_envelope_and_counts(engine, oracle):
     check_song(res[0], ref, tag="3min")
     E, Eo = engine.envelope_energy(pcm), oracle.envelope_energy(pcm)
     assert np.max(np.abs(E - Eo) / np.maximum(Eo, 1e-300)) <= 2.4e-7 and np.mean(E == Eo) > 0.99
+
+
+# ---------------------------------------------------------------- envelope accumulation chain: edge cases
+def _tonal_song(seed, seconds, freq, noise):
+    """A strong sinusoid over very quiet noise: the hop spectra put nearly all their energy into one
+    bin, so the float accumulation jumps several binades at once (multi-binade crossings)."""
+    rng = np.random.default_rng(seed)
+    n = int(22050 * seconds)
+    t = np.arange(n) / 22050.0
+    mono = 12000.0 * np.sin(2 * np.pi * freq * t) * (0.6 + 0.4 * np.sin(2 * np.pi * 1.7 * t)) + noise * rng.standard_normal(n)
+    pcm = np.empty(2 * n, dtype=np.int16)
+    pcm[0::2] = np.clip(np.rint(mono), -32768, 32767)
+    pcm[1::2] = np.clip(np.rint(mono * 0.93), -32768, 32767)
+    return pcm
+
+
+def test_envelope_chain_tonal_and_quiet_songs(engine, oracle):
+    cases = [_tonal_song(1, 7.0, 3000.0, 2.0), _tonal_song(2, 5.0, 9000.0, 0.6), _tonal_song(3, 6.0, 150.0, 30.0),
+             (song_s16(71, 6.0, decorrelate=True).astype(np.int32) // 300).astype(np.int16)]  # a very quiet song
+    for i, pcm in enumerate(cases):
+        E, Eo = engine.envelope_energy(pcm), oracle.envelope_energy(pcm)
+        assert np.max(np.abs(E - Eo) / np.maximum(Eo, 1e-300)) <= 2.4e-7, i
+        assert np.mean(E == Eo) > 0.98, (i, float(np.mean(E == Eo)))
+        res = engine.analyze_s16([pcm], [max(1, len(pcm) // 44100)])
+        check_song(res[0], oracle.analyze(pcm, max(1, len(pcm) // 44100)), tag=f"tonal {i}")
+
+
+def test_envelope_fast_chain_equals_slow_chain(engine):
+    """The predicted-binade accumulation and its fallback (binade-by-binade scan) are the same function:
+    forcing the fallback for every hop changes no bit of E[m], for native int16 and for float32 input."""
+    songs = [song_s16(81, 12.0, decorrelate=True), _tonal_song(4, 4.0, 5000.0, 1.0), song_s16(82, 3.1, gain=0.05)]
+    f32 = [song_f32(83, 6.0), song_f32(84, 3.3)]
+    fast = [engine.envelope_energy(p) for p in songs]
+    fast_rec = engine.analyze_f32(f32)
+    engine.debug_flags(bliss_b200.engine.DEBUG_SLOW_CHAIN)
+    try:
+        slow = [engine.envelope_energy(p) for p in songs]
+        slow_rec = engine.analyze_f32(f32)
+    finally:
+        engine.debug_flags(0)
+    for a, b in zip(fast, slow):
+        assert np.array_equal(a, b)
+    assert fast_rec.tobytes() == slow_rec.tobytes()
+
+
+def test_envelope_hop_counts_around_warp_and_cta_boundaries(engine, oracle):
+    """A warp owns 32 hops and a CTA 256 (n_hops = 2 F - 2 is always even): songs whose hop count ends
+    just before / on / after those boundaries."""
+    for n_hops in (18, 30, 32, 34, 62, 64, 66, 254, 256, 258, 290):
+        F = (n_hops + 2) // 2
+        pcm = np.resize(song_s16(500 + n_hops, 1.0, decorrelate=True), 512 * F + 37)
+        E, Eo = engine.envelope_energy(pcm), oracle.envelope_energy(pcm)
+        assert E.shape == Eo.shape == (2 * F,)
+        assert np.max(np.abs(E - Eo) / np.maximum(Eo, 1e-300)) <= 2.4e-7, n_hops
+        assert np.all(E[:n_hops] > 0) and np.all(E[n_hops:] == 0), n_hops
+
+
+def test_f32_song_is_independent_of_its_neighbours(engine):
+    """The tensor copies of pass 1 also bring in rows of the neighbouring songs (FIR halo); they must read
+    as zeros: a float32 song gives the same record alone, first, last or in the middle of a batch."""
+    x = song_f32(91, 5.0)
+    a, b = song_f32(92, 2.0), (song_f32(93, 3.0) * 3.0).astype(np.float32)
+    alone = engine.analyze_f32([x])[0].tobytes()
+    assert engine.analyze_f32([x, a, b])[0].tobytes() == alone
+    assert engine.analyze_f32([a, x, b])[1].tobytes() == alone
+    assert engine.analyze_f32([b, a, x])[2].tobytes() == alone
