@@ -264,6 +264,10 @@ __device__ __forceinline__ double float_chain(double *xr, int lane16, bool activ
     }
     double excl = __shfl_up_sync(full, inc, 1, 16);
     if (lane16 == 0) excl = 0.0;
+    // Nothing left to add after bin 16 (digital silence, or bins below half a double ulp of the sum): the
+    // chain ends at r16. (Without this a silent hop, whose sum never becomes a normal float, would take the
+    // slow path one bin at a time.)
+    const bool rest_zero = __shfl_sync(full, inc, 15, 16) == __shfl_sync(full, inc, 0, 16);
     // every bin at its predicted grid; crossing bins and lane 0's bins (already in r16) count nothing
     const bool mine = active && lane16 != 0;
     int hprev = __double2hiint(excl);
@@ -333,6 +337,7 @@ __device__ __forceinline__ double float_chain(double *xr, int lane16, bool activ
     const unsigned qf = q + (*reinterpret_cast<const unsigned *>(aux + kAuxTot) - Pprev);
     ok = ok && (!active || (qf < (1u << 24) && *reinterpret_cast<const int *>(aux + kAuxEnd) == ex && ex <= 1023 + 126));
     double r = __hiloint2double((ex << 20) | (int)((qf & 0x7FFFFFu) >> 3), (int)((qf & 7u) << 29));
+    if (rest_zero) { r = r16; ok = true; }
     if (__any_sync(full, !ok) || force_slow) r = float_chain_rounds(xr, lane16, active, r16);
     return r;
 }

@@ -86,10 +86,16 @@ __global__ void __launch_bounds__(kEpThreads) epilogue_kernel(EpilogueParams p) 
             out.status |= BLX_SONG_SILENT;
             out.amplitude = nanf("");
         } else {
+            // Pass 1 counted every sample; the reference skips the zeros in front of the first and behind the
+            // last non-zero sample (reference src/amplitude_sort.c:26-39), and its float counters stop at 2^24
+            // (x + 1 == x from there on).
             const unsigned *gh = p.hist + (size_t)s * kHistStride;
+            const unsigned trimmed = (unsigned)first_nz + (unsigned)(sd.n_samples - 1 - last_nz);
             for (int i = tid; i < kSmW; i += kEpThreads) {
                 const int b = i - 3;
-                hA[i] = (b >= 0 && b < kHistBins) ? (float)gh[b] : 0.0f;
+                unsigned c = (b >= 0 && b < kHistBins) ? gh[b] : 0u;
+                if (b == 32768 - kHistLo) c -= trimmed;
+                hA[i] = (float)min(c, 1u << 24);
                 hB[i] = 0.0f;
             }
             __syncthreads();

@@ -335,3 +335,33 @@ def test_f32_song_is_independent_of_its_neighbours(engine):
     assert engine.analyze_f32([x, a, b])[0].tobytes() == alone
     assert engine.analyze_f32([a, x, b])[1].tobytes() == alone
     assert engine.analyze_f32([b, a, x])[2].tobytes() == alone
+
+
+def test_song_with_silent_passages(engine, oracle):
+    """Digital silence inside a song: hop energies of exactly zero (the accumulation never becomes a normal
+    float) next to ordinary hops."""
+    pcm = song_s16(95, 8.0, decorrelate=True)
+    pcm[2 * 22050 * 2:2 * 22050 * 4] = 0  # seconds 2..4 silent
+    pcm[:5001] = 0   # the reference's amplitude analyser skips the zeros in front of the first ...
+    pcm[-3000:] = 0  # ... and behind the last non-zero sample (reference src/amplitude_sort.c:26-31)
+    E, Eo = engine.envelope_energy(pcm), oracle.envelope_energy(pcm)
+    assert np.array_equal(E == 0, Eo == 0)
+    assert np.max(np.abs(E - Eo) / np.maximum(Eo, 1e-300)) <= 2.4e-7
+    res = engine.analyze_s16([pcm], [8])
+    check_song(res[0], oracle.analyze(pcm, 8), tag="silent passages")
+
+
+def test_leading_and_trailing_silence_f32(engine, oracle):
+    """Float32 input that starts and ends with digital silence (the trimmed zeros must not be counted in the
+    amplitude histogram), plus a song whose only sound is in the middle."""
+    x = song_f32(96, 6.0)
+    x[:7001] = 0.0
+    x[-9000:] = 0.0
+    y = np.zeros(5 * 44100, dtype=np.float32)
+    y[60000:150000] = song_f32(97, 5.0)[60000:150000]
+    res = engine.analyze_f32([x, y])
+    for i, z in enumerate([x, y]):
+        pcm = oracle.frontend_f32(z)
+        ref = oracle.analyze(pcm, len(z) // 44100)
+        check_song(res[i], ref, tag=f"silence f32 {i}")
+        assert float(res[i]["amplitude"]) == ref["amplitude"], i

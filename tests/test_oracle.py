@@ -77,6 +77,18 @@ def test_oracle_bit_identical_to_reference_sources(oracle, reflib, seed):
     assert a["calm_or_loud"] == b["calm_or_loud"]
 
 
+def test_oracle_silence_trimming_matches_reference(oracle, reflib):
+    """Zeros in front of the first and behind the last non-zero sample are skipped by the amplitude
+    analyser (reference src/amplitude_sort.c:26-39); silence inside the song is not."""
+    pcm = song_s16(13, 6.0, decorrelate=True)
+    pcm[:5001] = 0
+    pcm[-3000:] = 0
+    pcm[100000:160000] = 0
+    a, b = oracle.analyze(pcm, 6), reflib.bl_analyze(pcm, 6)
+    for k in ("tempo", "amplitude", "frequency", "attack", "force"):
+        assert _bits(a[k]) == _bits(b[k]), (k, a[k], b[k])
+
+
 def test_oracle_mono_branch_matches_reference(oracle, reflib):
     pcm = song_s16(11, 3.0)[::2].copy()  # reference src/frequency_sort.c:76-80
     s, keep = reflib.make_song(pcm, 3, channels=1)
