@@ -5,6 +5,7 @@ CUDA). Importing it never falls back to a CPU implementation: without the built 
 `load()` raises, without a B200 `Engine()` raises.
 """
 from ._lib import LIB_PATH, BlSong, BlxResult, EnvelopeResult, ForceVector, load  # noqa: F401
+from . import compat  # noqa: F401  (the reference's Python package surface)
 from .engine import (ALIGN_ELEMS, DO_ALL, DO_AMPLITUDE, DO_ENVELOPE, DO_FREQUENCY, FMT_F32, FMT_S16,  # noqa: F401
                      RESULT_DTYPE, BlxError, Engine)
 
