@@ -465,8 +465,8 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                 double u[16];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    u[2 * i] = int_to_double_exact((int)(short)(wds[i] & 0xffff));
-                    u[2 * i + 1] = int_to_double_exact(wds[i] >> 16);
+                    u[2 * i] = (double)(short)(wds[i] & 0xffff);
+                    u[2 * i + 1] = (double)(short)(wds[i] >> 16);
                 }
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
@@ -490,8 +490,8 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                     const int wds[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        xv[8 * i + 2 * j] = int_to_double_exact((int)(short)(wds[j] & 0xffff));
-                        xv[8 * i + 2 * j + 1] = int_to_double_exact(wds[j] >> 16);
+                        xv[8 * i + 2 * j] = (double)(short)(wds[j] & 0xffff);
+                        xv[8 * i + 2 * j + 1] = (double)(short)(wds[j] >> 16);
                     }
                 }
 #pragma unroll
@@ -538,8 +538,8 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                 const int wds[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    X[8 * i + 2 * j] = int_to_double_exact((int)(short)(wds[j] & 0xffff));
-                    X[8 * i + 2 * j + 1] = int_to_double_exact(wds[j] >> 16);
+                    X[8 * i + 2 * j] = (double)(short)(wds[j] & 0xffff);
+                    X[8 * i + 2 * j + 1] = (double)(short)(wds[j] >> 16);
                 }
             }
             double corr = 0.0;
