@@ -26,6 +26,8 @@
 // At the end the eight per-group accumulators are reduced in a fixed order into one partial spectrum
 // per CTA; the epilogue kernel (epilogue.cu) sums the partials of a song in order, so results are
 // deterministic run to run.
+#include <type_traits>
+
 #include "blx_common.cuh"
 #include "fft16.cuh"
 #include "kernels.h"
@@ -228,74 +230,106 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant
                 w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
                 w[12 + 4 * i] = b.x; w[12 + 4 * i + 1] = b.y; w[12 + 4 * i + 2] = b.z; w[12 + 4 * i + 3] = b.w;
             }
-            short qv[32];
-            int row_sum = 0;
-            unsigned long long row_sq = 0ull;
             const int valid = (int)max(0ll, min(32ll, n_out - m0)); // samples of this row inside the song
+            // The row in two compiled forms: CHECK = false for a row entirely inside the song (no per-sample
+            // test), CHECK = true for the one row a song ends in (and the rows behind it).
+            auto do_row = [&](auto check_tag) {
+                constexpr bool CHECK = decltype(check_tag)::value;
+                int qw[16]; // the row's 32 int16 values, packed in pairs (what goes to the decimated stream)
+                int row_sum = 0;
+                unsigned sq_lo = 0, sq_hi = 0; // 64-bit sum of squares
+                int first_i = 64, last_i = -1;  // first / last non-zero sample of the row (CHECK rows, or zero ends)
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
+                for (int s = 0; s < 8; ++s) {
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    const int q4 = 2 * s + 3 + h2;
-                    const float4 a = (q4 < 16) ? own(q4) : *swz_chunk(ra + SM::f32_half, ka1, q4 - 16);
-                    w[24 + 4 * h2] = a.x; w[25 + 4 * h2] = a.y; w[26 + 4 * h2] = a.z; w[27 + 4 * h2] = a.w;
-                }
-                float o[4];
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int q4 = 2 * s + 3 + h2;
+                        const float4 a = (q4 < 16) ? own(q4) : *swz_chunk(ra + SM::f32_half, ka1, q4 - 16);
+                        w[24 + 4 * h2] = a.x; w[25 + 4 * h2] = a.y; w[26 + 4 * h2] = a.z; w[27 + 4 * h2] = a.w;
+                    }
+                    float o[4];
+                    int qi[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c = 12 + 2 * u;
-                    float acc = __fmul_rn(BLX_FE_CENTER, w[c]);
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = 12 + 2 * u;
+                        float acc = __fmul_rn(BLX_FE_CENTER, w[c]);
 #pragma unroll
-                    for (int k = 0; k < BLX_FE_NPAIRS; ++k)
-                        acc = __fmaf_rn(H[k], __fadd_rn(w[c - (2 * k + 1)], w[c + (2 * k + 1)]), acc);
-                    float q = rintf(acc);
-                    q = fminf(fmaxf(q, -32768.0f), 32767.0f);
-                    o[u] = q;
+                        for (int k = 0; k < BLX_FE_NPAIRS; ++k)
+                            acc = __fmaf_rn(H[k], __fadd_rn(w[c - (2 * k + 1)], w[c + (2 * k + 1)]), acc);
+                        float q = rintf(acc);
+                        q = fminf(fmaxf(q, -32768.0f), 32767.0f);
+                        o[u] = q;
+                        if (FULL) qi[u] = (int)q;
+                    }
                     if (FULL) {
-                        const int qi = (int)q;
-                        qv[4 * s + u] = (short)qi;
-                        if (4 * s + u < valid) { // mono sample -> L = R: every value counts twice
-                            row_sum += qi;
-                            row_sq += (unsigned long long)(unsigned)(qi * qi);
-                            hist_add(hist, qi, 2u);
+                        qw[2 * s] = (qi[0] & 0xffff) | (qi[1] << 16);
+                        qw[2 * s + 1] = (qi[2] & 0xffff) | (qi[3] << 16);
+                        if (!CHECK) {
+                            // mono sample -> L = R: every value counts twice (doubled below / in the histogram)
+                            row_sum += (qi[0] + qi[1]) + (qi[2] + qi[3]);
+                            const unsigned a = (unsigned)(qi[0] * qi[0]) + (unsigned)(qi[1] * qi[1]); // <= 2^31
+                            const unsigned b = (unsigned)(qi[2] * qi[2]) + (unsigned)(qi[3] * qi[3]);
+                            const unsigned t0 = sq_lo + a;
+                            sq_hi += (t0 < a);
+                            sq_lo = t0 + b;
+                            sq_hi += (sq_lo < b);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) hist_add(hist, qi[u], 2u);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (4 * s + u < valid) {
+                                    row_sum += qi[u];
+                                    const unsigned a = (unsigned)(qi[u] * qi[u]);
+                                    sq_lo += a;
+                                    sq_hi += (sq_lo < a);
+                                    hist_add(hist, qi[u], 2u);
+                                    if (qi[u] != 0) { first_i = min(first_i, 4 * s + u); last_i = 4 * s + u; }
+                                }
+                            }
                         }
                     }
-                }
-                const float4 hv = *reinterpret_cast<const float4 *>(hrow + 4 * s);
-                float4 r4;
-                r4.x = o[0] * hv.x; r4.y = o[1] * hv.y; r4.z = o[2] * hv.z; r4.w = o[3] * hv.w;
-                *reinterpret_cast<float4 *>(fout + 4 * s) = r4;
+                    const float4 hv = *reinterpret_cast<const float4 *>(hrow + 4 * s);
+                    float4 r4;
+                    r4.x = o[0] * hv.x; r4.y = o[1] * hv.y; r4.z = o[2] * hv.z; r4.w = o[3] * hv.w;
+                    *reinterpret_cast<float4 *>(fout + 4 * s) = r4;
 #pragma unroll
-                for (int i = 0; i < 24; ++i) w[i] = w[i + 8];
-            }
-            if (FULL && m0 < n_out) {
-                ts.sum += 2 * (long long)row_sum;
-                ts.sumsq += 2ull * row_sq;
-                // first / last non-zero sample (interleaved index 2 t, 2 t + 1): the row's end samples
-                // decide unless one of them is zero or past the song's end (then scan the row)
-                if (valid == 32 && qv[0] != 0 && qv[31] != 0) {
-                    ts.first_nz = min(ts.first_nz, (int)(2 * m0));
-                    ts.last_nz = max(ts.last_nz, (int)(2 * (m0 + 31) + 1));
-                } else {
-                    for (int i = 0; i < valid; ++i)
-                        if (qv[i] != 0) {
-                            ts.first_nz = min(ts.first_nz, (int)(2 * (m0 + i)));
-                            ts.last_nz = max(ts.last_nz, (int)(2 * (m0 + i) + 1));
+                    for (int i = 0; i < 24; ++i) w[i] = w[i + 8];
+                }
+                if (FULL && (!CHECK || valid > 0)) {
+                    ts.sum += 2 * (long long)row_sum;
+                    ts.sumsq += 2ull * (((unsigned long long)sq_hi << 32) | sq_lo);
+                    // first / last non-zero sample (interleaved index 2 t, 2 t + 1): the row's end samples decide
+                    // unless one of them is zero (then look through the row)
+                    if (!CHECK) {
+                        if ((qw[0] & 0xffff) != 0 && (qw[15] >> 16) != 0) {
+                            first_i = 0;
+                            last_i = 31;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int v = (i & 1) ? (qw[i >> 1] >> 16) : (qw[i >> 1] & 0xffff);
+                                if (v != 0) { first_i = min(first_i, i); last_i = i; }
+                            }
                         }
-                }
-            }
-            if (FULL && m0 < n_out) { // decimated stream for the envelope pass (mono: L == R)
-                // two 256-bit stores (STG.256: a full 32-byte sector per lane); q rows are padded to 32 samples by the engine
-                short *dst = p.qout + sd.q_off + m0;
-                const int4 *srcq = reinterpret_cast<const int4 *>(qv);
+                    }
+                    if (last_i >= 0) {
+                        ts.first_nz = min(ts.first_nz, (int)(2 * (m0 + first_i)));
+                        ts.last_nz = max(ts.last_nz, (int)(2 * (m0 + last_i) + 1));
+                    }
+                    // decimated stream for the envelope pass (mono: L == R): two 256-bit stores (STG.256: a full
+                    // 32-byte sector per lane); q rows are padded to 32 samples by the engine
+                    short *dst = p.qout + sd.q_off + m0;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int4 a = srcq[2 * i], b = srcq[2 * i + 1];
-                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * i), "r"(a.x), "r"(a.y),
-                                 "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                                 : "memory");
+                    for (int i = 0; i < 2; ++i)
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * i), "r"(qw[8 * i]),
+                                     "r"(qw[8 * i + 1]), "r"(qw[8 * i + 2]), "r"(qw[8 * i + 3]), "r"(qw[8 * i + 4]), "r"(qw[8 * i + 5]),
+                                     "r"(qw[8 * i + 6]), "r"(qw[8 * i + 7])
+                                     : "memory");
                 }
-            }
+            };
+            if (!FULL || valid == 32) do_row(std::false_type{});
+            else do_row(std::true_type{});
         } else {
             const int4 *rowp = reinterpret_cast<const int4 *>(raw + (size_t)tid * SM::row_stride);
             constexpr int per_vec = (KIND == kInS16Stereo) ? 4 : 8; // per-channel samples per 16-byte load
