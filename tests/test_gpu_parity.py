@@ -56,6 +56,16 @@ def test_bl_analyze_golden_fixture(oracle):
     assert rel(got["frequency"], ref["frequency"]) <= 1e-5
 
 
+def test_second_golden_fixture_s32(engine):
+    """reference tests/test_analyze.c:59-78: audio/song_s32.flac after the reference's decode + resample
+    (fixture tests/golden/song_s32_pcm.npz, md5-pinned): force vector within the reference's own 1e-5, beat 61."""
+    from test_oracle import GOLDEN_S32, load_s32_pcm
+    res = engine.analyze_s16([load_s32_pcm()], [GOLDEN_S32["duration"]])[0]
+    assert res["status"] == 0 and int(res["beat"]) == GOLDEN_S32["beat"] and int(res["calm_or_loud"]) == 1
+    for k in ("force", "tempo", "amplitude", "frequency", "attack"):
+        assert abs(float(res[k]) - GOLDEN_S32[k]) <= 1e-5, (k, float(res[k]), GOLDEN_S32[k])
+
+
 # ---------------------------------------------------------------- native int16 input
 S16_CASES = [(0, 6.0, False, 1.0), (1, 11.3, True, 0.4), (2, 3.0, True, 0.02), (3, 20.0, False, 1.6),
              (4, 2.0, True, 0.9), (5, 33.0, False, 0.7)]

@@ -15,6 +15,18 @@ GOLDEN_S16 = dict(force=-20.777929, tempo=-8.945454, amplitude=-10.641844, frequ
                   attack=-15.560563, nSamples=488138, duration=11, beat=59)
 # reference tests/test_decode.c:16-17
 GOLDEN_S16_MD5 = "8a1bd824951c0433cc47fec5bf41d0a9"
+# reference tests/test_analyze.c:59-78 (audio/song_s32.flac, 48 kHz / 24 bit, through libswresample) and
+# tests/test_decode.c:35-36; the decoded PCM is the committed fixture made by tools/make_golden_s32.py
+GOLDEN_S32 = dict(force=-20.821571, tempo=-8.218182, amplitude=-10.641695, frequency=-10.179875,
+                  attack=-15.561186, nSamples=488140, duration=11, beat=61)
+GOLDEN_S32_MD5 = "eb9f31a7b9ed022d66ff82b76e7c3c18"
+
+
+def load_s32_pcm():
+    pcm = np.load(os.path.join(GOLDEN_DIR, "song_s32_pcm.npz"))["pcm"]
+    assert pcm.dtype == np.int16 and len(pcm) == GOLDEN_S32["nSamples"]
+    assert hashlib.md5(pcm.tobytes()).hexdigest() == GOLDEN_S32_MD5
+    return pcm
 
 
 @pytest.fixture(scope="module")
@@ -59,6 +71,16 @@ def test_reference_sources_reproduce_golden_vector(reflib, song_pcm):
     assert r["rc"] == 1
     for k in ("force", "tempo", "amplitude", "frequency", "attack"):
         assert abs(r[k] - GOLDEN_S16[k]) <= 1e-5, (k, r[k], GOLDEN_S16[k])
+
+
+def test_second_golden_vector_s32(oracle, reflib):
+    """The reference's second fixture: both checkers reproduce its pinned force vector (abs 1e-5, reference
+    tests/test_analyze.c:5-11) from the PCM the reference's decoder produces (md5-pinned)."""
+    pcm = load_s32_pcm()
+    for r in (oracle.analyze(pcm, GOLDEN_S32["duration"]), reflib.bl_analyze(pcm, GOLDEN_S32["duration"])):
+        for k in ("force", "tempo", "amplitude", "frequency", "attack"):
+            assert abs(r[k] - GOLDEN_S32[k]) <= 1e-5, (k, r[k], GOLDEN_S32[k])
+    assert oracle.analyze(pcm, GOLDEN_S32["duration"])["beat"] == GOLDEN_S32["beat"]
 
 
 def _bits(x):
