@@ -448,6 +448,12 @@ def run_ours(args):
 
     # ---------------- e2e: host buffers through the C-ABI, copies inside the timed region
     Be = min(args.e2e_songs, B)
+    try:  # every rank pins its own songs: keep the ranks of one box within half of the host memory that is free
+        import psutil
+        fit = int(0.5 * psutil.virtual_memory().available / max(world, 1) / (stride * 4))
+        Be = max(8, min(Be, fit))
+    except Exception:
+        pass
     pinned = torch.empty(Be * stride, dtype=torch.float32, pin_memory=True)
     pinned.copy_(buf[:Be * stride])
     torch.cuda.synchronize()

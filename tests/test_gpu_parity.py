@@ -375,3 +375,27 @@ def test_leading_and_trailing_silence_f32(engine, oracle):
         ref = oracle.analyze(pcm, len(z) // 44100)
         check_song(res[i], ref, tag=f"silence f32 {i}")
         assert float(res[i]["amplitude"]) == ref["amplitude"], i
+
+
+def test_large_ragged_batch_properties(engine, oracle):
+    """A few hundred float32 songs of mixed lengths in one call (several pass-1 parts, envelope CTAs and warps
+    per song; duplicates; shuffled order): every record depends on its song alone - duplicates are
+    byte-identical, a permutation of the batch permutes the records - and a sample of them matches the oracle."""
+    rng = np.random.default_rng(2024)
+    base = [song_f32(700 + i, float(s)) for i, s in enumerate(rng.uniform(1.2, 24.0, size=48))]
+    base.append(song_f32(760, 95.0))  # several envelope CTAs and pass-1 parts
+    order = rng.integers(0, len(base), size=320)
+    batch = [base[i] for i in order]
+    res = engine.analyze_f32(batch)
+    first = {}
+    for pos, i in enumerate(order):
+        if i in first:
+            assert res[pos].tobytes() == res[first[i]].tobytes(), (pos, i)
+        else:
+            first[i] = pos
+    perm = rng.permutation(len(batch))
+    res2 = engine.analyze_f32([batch[j] for j in perm])
+    assert res2.tobytes() == res[perm].tobytes()
+    for i in (0, 7, 19, 48):
+        x = base[i]
+        check_song(res[first[i]], oracle.analyze(oracle.frontend_f32(x), len(x) // 44100), tag=f"large batch song {i}")
