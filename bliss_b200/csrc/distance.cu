@@ -69,23 +69,46 @@ __global__ void __launch_bounds__(kDistThreads) distance_rows_kernel(const float
 }
 
 // Fused epilogue: nearest other song (and optionally the row sum), nothing materialised.
-// CTA = 256 threads x 2 rows each; the column vectors stream through shared memory in tiles of 2048, so
-// every column is read from L2 once per 512 rows and from shared memory as a warp-wide broadcast.
+// CTA = 256 threads x 4 rows each; the column vectors stream through shared memory in tiles of 1024, every
+// component stored twice side by side, so that one 64-bit register pair holds (b.x, b.x): the squared
+// distances of two rows to one column are then computed with the packed single-precision instructions of
+// sm_100 for the differences and the sums (sub/add.rn.f32x2 -> FADD2: two IEEE round-to-nearest operations per
+// instruction; the squares are scalar FMULs, see sq2), so each lane is bit-identical to the scalar reference sequence. Every column is read from L2 once
+// per 1024 rows and from shared memory as a warp-wide broadcast.
 // The nearest neighbour is decided on the squared distance s (float, reference operation order); the
 // correctly rounded sqrt is taken only for the rare candidates with s <= best s. sqrt is monotone, so a
 // candidate with a larger s can never have a strictly smaller distance; candidates that tie after
 // rounding keep the lowest index (columns are visited in increasing order), exactly what a scan over
 // bl_distance values gives.
 namespace {
-constexpr int kNearRows = 2;
-constexpr int kNearTile = 2048;
+constexpr int kNearRows = 4;
+constexpr int kNearTile = 1024;
+typedef unsigned long long f32x2; // (lo, hi) = two floats
 
-__device__ __forceinline__ float sqdist_pair(const float4 a, const float4 b) {
-    const float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y), d2 = __fsub_rn(a.z, b.z), d3 = __fsub_rn(a.w, b.w);
-    float s = __fmul_rn(d0, d0);
-    s = __fadd_rn(s, __fmul_rn(d1, d1));
-    s = __fadd_rn(s, __fmul_rn(d2, d2));
-    s = __fadd_rn(s, __fmul_rn(d3, d3));
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// The squares stay scalar: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 - which rounds
+// once instead of twice - whatever --fmad says and however the two are spelled (it also folds
+// fma(a, b, -0) / fma(a, 1, b) back first); a scalar mul.rn.f32 is never contracted.
+__device__ __forceinline__ f32x2 sq2(f32x2 d) {
+    float lo, hi;
+    unpack2(d, lo, hi);
+    return pack2(__fmul_rn(lo, lo), __fmul_rn(hi, hi));
+}
+
+// squared distances of two rows (packed per component in ax..aw) to the column (bx..bw, each component twice)
+__device__ __forceinline__ f32x2 sqdist2(f32x2 ax, f32x2 ay, f32x2 az, f32x2 aw, f32x2 bx, f32x2 by, f32x2 bz, f32x2 bw) {
+    const f32x2 d0 = sub2(ax, bx), d1 = sub2(ay, by), d2 = sub2(az, bz), d3 = sub2(aw, bw);
+    f32x2 s = sq2(d0);
+    s = add2(s, sq2(d1));
+    s = add2(s, sq2(d2));
+    s = add2(s, sq2(d3));
     return s;
 }
 } // namespace
@@ -95,38 +118,57 @@ __global__ void __launch_bounds__(kDistThreads) distance_nearest_kernel(const fl
                                                                         int n_rows, int *__restrict__ idx_out,
                                                                         float *__restrict__ dist_out,
                                                                         double *__restrict__ sum_out) {
-    __shared__ float4 cols[kNearTile];
+    __shared__ __align__(16) f32x2 cols[kNearTile][4]; // (x,x) (y,y) (z,z) (w,w)
     const float inf = __int_as_float(0x7f800000);
     int row[kNearRows];
-    float4 a[kNearRows];
+    f32x2 ax[kNearRows / 2], ay[kNearRows / 2], az[kNearRows / 2], aw[kNearRows / 2];
     float best_s[kNearRows], best_d[kNearRows];
     int best_j[kNearRows];
     double sum[kNearRows];
+    {
+        float4 a[kNearRows];
 #pragma unroll
-    for (int r = 0; r < kNearRows; ++r) {
-        const int lr = (blockIdx.x * kNearRows + r) * kDistThreads + threadIdx.x; // row inside the slab
-        row[r] = (lr < n_rows) ? row0 + lr : -1;
-        a[r] = (row[r] >= 0) ? v[row[r]] : make_float4(0, 0, 0, 0);
-        best_s[r] = inf; best_d[r] = inf; best_j[r] = -1; sum[r] = 0.0;
+        for (int r = 0; r < kNearRows; ++r) {
+            const int lr = (blockIdx.x * kNearRows + r) * kDistThreads + threadIdx.x; // row inside the slab
+            row[r] = (lr < n_rows) ? row0 + lr : -1;
+            a[r] = (row[r] >= 0) ? v[row[r]] : make_float4(0, 0, 0, 0);
+            best_s[r] = inf; best_d[r] = inf; best_j[r] = -1; sum[r] = 0.0;
+        }
+#pragma unroll
+        for (int h = 0; h < kNearRows / 2; ++h) {
+            ax[h] = pack2(a[2 * h].x, a[2 * h + 1].x); ay[h] = pack2(a[2 * h].y, a[2 * h + 1].y);
+            az[h] = pack2(a[2 * h].z, a[2 * h + 1].z); aw[h] = pack2(a[2 * h].w, a[2 * h + 1].w);
+        }
     }
     for (int c0 = 0; c0 < n; c0 += kNearTile) {
         const int cn = min(kNearTile, n - c0);
         __syncthreads();
-        for (int i = threadIdx.x; i < cn; i += kDistThreads) cols[i] = v[c0 + i];
+        for (int i = threadIdx.x; i < cn; i += kDistThreads) {
+            const float4 b = v[c0 + i];
+            cols[i][0] = pack2(b.x, b.x); cols[i][1] = pack2(b.y, b.y);
+            cols[i][2] = pack2(b.z, b.z); cols[i][3] = pack2(b.w, b.w);
+        }
         __syncthreads();
         float part[kNearRows];
 #pragma unroll
         for (int r = 0; r < kNearRows; ++r) part[r] = 0.0f;
 #pragma unroll 4
         for (int i = 0; i < cn; ++i) {
-            const float4 b = cols[i];
+            const ulonglong2 b01 = *reinterpret_cast<const ulonglong2 *>(&cols[i][0]);
+            const ulonglong2 b23 = *reinterpret_cast<const ulonglong2 *>(&cols[i][2]);
 #pragma unroll
-            for (int r = 0; r < kNearRows; ++r) {
-                const float s = sqdist_pair(a[r], b);
-                if (WITH_SUM) part[r] += __fsqrt_rn(s);
-                if (s <= best_s[r] && c0 + i != row[r]) {
-                    const float d = __fsqrt_rn(s);
-                    if (d < best_d[r]) { best_d[r] = d; best_s[r] = s; best_j[r] = c0 + i; }
+            for (int h = 0; h < kNearRows / 2; ++h) {
+                float s2[2];
+                unpack2(sqdist2(ax[h], ay[h], az[h], aw[h], b01.x, b01.y, b23.x, b23.y), s2[0], s2[1]);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int r = 2 * h + q;
+                    const float s = s2[q];
+                    if (WITH_SUM) part[r] += __fsqrt_rn(s);
+                    if (s <= best_s[r] && c0 + i != row[r]) {
+                        const float d = __fsqrt_rn(s);
+                        if (d < best_d[r]) { best_d[r] = d; best_s[r] = s; best_j[r] = c0 + i; }
+                    }
                 }
             }
         }
