@@ -408,6 +408,37 @@ def run_ours(args):
                                      "unit": "GB/s", "frac": gbs / hbm_peak, "ms_per_launch": k_ms,
                                      "alg_bytes_per_launch": Bs * n30 * 4, "peak_source": peak_src}}
 
+    # ---------------- the analysers' native input (int16 / 22 050 Hz / stereo, what the reference's decoder hands over):
+    # the same songs after the front-end, full pipeline without it; informational (the metric is the float32 workload)
+    native = None
+    if args.s16_songs > 0:
+        Bn = min(args.s16_songs, B)
+        n16 = 2 * (n_in // 2)                       # interleaved L,R
+        stride16 = (n16 + 63) // 64 * 64 + 64
+        s16 = torch.zeros(Bn * stride16, dtype=torch.int16, device=dev)
+        for i in range(Bn):
+            mono = torch.clamp(torch.round(buf[i * stride:i * stride + n_in:2][:n16 // 2] * 32768.0), -32768, 32767).to(torch.int16)
+            view = s16[i * stride16:i * stride16 + n16].view(-1, 2)
+            view[:, 0] = mono
+            view[:, 1] = torch.roll(mono, 3)          # decorrelated right channel
+        o16, l16 = [i * stride16 for i in range(Bn)], [n16] * Bn
+        durs = [int(args.seconds)] * Bn
+        d_out16 = torch.zeros(Bn * 8, dtype=torch.int32, device=dev)
+        for _ in range(3):
+            eng.analyze_device(E.FMT_S16, s16.data_ptr(), o16, l16, d_out16.data_ptr(), durations=durs, stream=stream)
+        barrier()
+        ev0.record()
+        for _ in range(3):
+            eng.analyze_device(E.FMT_S16, s16.data_ptr(), o16, l16, d_out16.data_ptr(), durations=durs, stream=stream)
+        ev1.record()
+        barrier()
+        ms16 = max_over_ranks(ev0.elapsed_time(ev1)) / 3
+        r16 = np.frombuffer(d_out16.cpu().numpy().tobytes(), dtype=bliss_b200.RESULT_DTYPE)
+        native = {"workload": f"{Bn} x {args.seconds:g}-s int16 / 22 050 Hz / stereo songs per GPU (the reference decoder's output "
+                              "format), full pipeline", "value": world * Bn / (ms16 * 1e-3), "unit": UNIT, "ms_per_pass": ms16,
+                  "bytes_per_song": n16 * 2, "all_status_ok": bool(np.all(r16["status"] == 0))}
+        del s16
+
     # ---------------- configs[3]/[4]: all-pairs bl_distance over 1 M force vectors, fused nearest-neighbour
     # epilogue; vectors are sharded by rank, all-gathered (NCCL, 16 B/song), each rank does its row slab
     all_pairs = None
@@ -513,7 +544,7 @@ def run_ours(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 (envelope) + f32 (spectrum) + int64 (statistics)", "data": "synthetic",
             "config": workload_config(args, B, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_kernels": kernels, "spectral_only": spectral, "all_pairs": all_pairs, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_kernels": kernels, "spectral_only": spectral, "native_s16": native, "all_pairs": all_pairs, "cpu_baseline": cpu_baseline,
             "parity": parity,
         }
         print(json.dumps(line), flush=True)
@@ -532,6 +563,7 @@ def main():
     ap.add_argument("--songs-per-step", type=int, default=2048)
     ap.add_argument("--seconds", type=float, default=180.0)
     ap.add_argument("--e2e-songs", type=int, default=256)
+    ap.add_argument("--s16-songs", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spectral", action="store_true")
     ap.add_argument("--no-distance", action="store_true")
