@@ -8,6 +8,8 @@
 // dot product and squared norms, double sqrt / multiply / divide, rounded to float.
 // Every operation below is an explicit round-to-nearest intrinsic, so the matrices are
 // bit-identical to the reference's scalar code.
+#include <algorithm>
+
 #include "blx_common.cuh"
 #include "kernels.h"
 
@@ -113,11 +115,17 @@ __device__ __forceinline__ f32x2 sqdist2(f32x2 ax, f32x2 ay, f32x2 az, f32x2 aw,
 }
 } // namespace
 
+// gridDim.y > 1 splits the columns into contiguous ranges of `cols_per_split` (a multiple of the tile), so that
+// a slab of few rows still fills the GPU (multi-GPU runs hand every rank n / world rows): the per-range
+// winners are then merged with one 64-bit atomicMin per row on (distance bits, index) - distances are
+// non-negative, so the packed order is "smaller distance, then lower index", the rule of the scan itself -
+// and nearest_unpack_kernel writes the two arrays. Row sums are only produced unsplit.
 template <bool WITH_SUM>
 __global__ void __launch_bounds__(kDistThreads) distance_nearest_kernel(const float4 *__restrict__ v, int n, int row0,
                                                                         int n_rows, int *__restrict__ idx_out,
                                                                         float *__restrict__ dist_out,
-                                                                        double *__restrict__ sum_out) {
+                                                                        double *__restrict__ sum_out, int cols_per_split,
+                                                                        unsigned long long *__restrict__ packed) {
     __shared__ __align__(16) f32x2 cols[kNearTile][4]; // (x,x) (y,y) (z,z) (w,w)
     const float inf = __int_as_float(0x7f800000);
     int row[kNearRows];
@@ -140,8 +148,9 @@ __global__ void __launch_bounds__(kDistThreads) distance_nearest_kernel(const fl
             az[h] = pack2(a[2 * h].z, a[2 * h + 1].z); aw[h] = pack2(a[2 * h].w, a[2 * h + 1].w);
         }
     }
-    for (int c0 = 0; c0 < n; c0 += kNearTile) {
-        const int cn = min(kNearTile, n - c0);
+    const int c_begin = blockIdx.y * cols_per_split, c_end = min(n, c_begin + cols_per_split);
+    for (int c0 = c_begin; c0 < c_end; c0 += kNearTile) {
+        const int cn = min(kNearTile, c_end - c0);
         __syncthreads();
         for (int i = threadIdx.x; i < cn; i += kDistThreads) {
             const float4 b = v[c0 + i];
@@ -156,18 +165,25 @@ __global__ void __launch_bounds__(kDistThreads) distance_nearest_kernel(const fl
         for (int i = 0; i < cn; ++i) {
             const ulonglong2 b01 = *reinterpret_cast<const ulonglong2 *>(&cols[i][0]);
             const ulonglong2 b23 = *reinterpret_cast<const ulonglong2 *>(&cols[i][2]);
+            float sq[kNearRows];
 #pragma unroll
-            for (int h = 0; h < kNearRows / 2; ++h) {
-                float s2[2];
-                unpack2(sqdist2(ax[h], ay[h], az[h], aw[h], b01.x, b01.y, b23.x, b23.y), s2[0], s2[1]);
+            for (int h = 0; h < kNearRows / 2; ++h)
+                unpack2(sqdist2(ax[h], ay[h], az[h], aw[h], b01.x, b01.y, b23.x, b23.y), sq[2 * h], sq[2 * h + 1]);
+            if (WITH_SUM) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int r = 2 * h + q;
-                    const float s = s2[q];
-                    if (WITH_SUM) part[r] += __fsqrt_rn(s);
-                    if (s <= best_s[r] && c0 + i != row[r]) {
-                        const float d = __fsqrt_rn(s);
-                        if (d < best_d[r]) { best_d[r] = d; best_s[r] = s; best_j[r] = c0 + i; }
+                for (int r = 0; r < kNearRows; ++r) part[r] += __fsqrt_rn(sq[r]);
+            }
+            // one (rarely taken) branch per column for all rows of the thread; the row's own column is sorted
+            // out inside (it always gets here: its s is 0)
+            bool cand = false;
+#pragma unroll
+            for (int r = 0; r < kNearRows; ++r) cand = cand | (sq[r] <= best_s[r]);
+            if (cand) {
+#pragma unroll
+                for (int r = 0; r < kNearRows; ++r) {
+                    if (sq[r] <= best_s[r] && c0 + i != row[r]) {
+                        const float d = __fsqrt_rn(sq[r]);
+                        if (d < best_d[r]) { best_d[r] = d; best_s[r] = sq[r]; best_j[r] = c0 + i; }
                     }
                 }
             }
@@ -181,10 +197,23 @@ __global__ void __launch_bounds__(kDistThreads) distance_nearest_kernel(const fl
     for (int r = 0; r < kNearRows; ++r) {
         if (row[r] < 0) continue;
         const int o = row[r] - row0;
+        if (packed) {
+            atomicMin(&packed[o], ((unsigned long long)__float_as_uint(best_d[r]) << 32) | (unsigned)best_j[r]);
+            continue;
+        }
         if (idx_out) idx_out[o] = best_j[r];
         if (dist_out) dist_out[o] = best_d[r];
         if (WITH_SUM) sum_out[o] = sum[r];
     }
+}
+
+__global__ void nearest_unpack_kernel(const unsigned long long *__restrict__ packed, int n_rows, int *__restrict__ idx_out,
+                                      float *__restrict__ dist_out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_rows) return;
+    const unsigned long long p = packed[o];
+    if (idx_out) idx_out[o] = (int)(unsigned)p;
+    if (dist_out) dist_out[o] = __uint_as_float((unsigned)(p >> 32));
 }
 
 cudaError_t launch_distance_rows(const float *d_vectors, int n, int row0, int n_rows, int mode, float *d_out,
@@ -196,14 +225,37 @@ cudaError_t launch_distance_rows(const float *d_vectors, int n, int row0, int n_
     return cudaGetLastError();
 }
 
+int distance_nearest_splits(int n, int n_rows, bool with_sum) {
+    if (with_sum || n <= 0 || n_rows <= 0) return 1;
+    const int rows_per_cta = kDistThreads * kNearRows;
+    const int row_blocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int want = (4 * sms + row_blocks - 1) / row_blocks;       // ~4 CTAs per SM
+    const int tiles = (n + kNearTile - 1) / kNearTile;
+    return std::max(1, std::min(want, std::min(tiles, 64)));
+}
+
 cudaError_t launch_distance_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_dist,
-                                    double *d_sum, cudaStream_t st) {
+                                    double *d_sum, unsigned long long *d_packed, int splits, cudaStream_t st) {
     if (n <= 0 || n_rows <= 0) return cudaSuccess;
     const int rows_per_cta = kDistThreads * kNearRows;
-    const unsigned grid = (unsigned)((n_rows + rows_per_cta - 1) / rows_per_cta);
+    const unsigned row_blocks = (unsigned)((n_rows + rows_per_cta - 1) / rows_per_cta);
     const float4 *v = reinterpret_cast<const float4 *>(d_vectors);
-    if (d_sum) distance_nearest_kernel<true><<<grid, kDistThreads, 0, st>>>(v, n, row0, n_rows, d_idx, d_dist, d_sum);
-    else distance_nearest_kernel<false><<<grid, kDistThreads, 0, st>>>(v, n, row0, n_rows, d_idx, d_dist, d_sum);
+    if (d_sum || splits <= 1 || !d_packed) {
+        if (d_sum) distance_nearest_kernel<true><<<row_blocks, kDistThreads, 0, st>>>(v, n, row0, n_rows, d_idx, d_dist, d_sum, n, nullptr);
+        else distance_nearest_kernel<false><<<row_blocks, kDistThreads, 0, st>>>(v, n, row0, n_rows, d_idx, d_dist, d_sum, n, nullptr);
+        return cudaGetLastError();
+    }
+    const int tiles = (n + kNearTile - 1) / kNearTile;
+    const int cols_per_split = (tiles + splits - 1) / splits * kNearTile;
+    const unsigned gy = (unsigned)((n + cols_per_split - 1) / cols_per_split);
+    cudaError_t e = cudaMemsetAsync(d_packed, 0xFF, (size_t)n_rows * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    distance_nearest_kernel<false><<<dim3(row_blocks, gy), kDistThreads, 0, st>>>(v, n, row0, n_rows, nullptr, nullptr, nullptr,
+                                                                                   cols_per_split, d_packed);
+    nearest_unpack_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(d_packed, n_rows, d_idx, d_dist);
     return cudaGetLastError();
 }
 

@@ -91,7 +91,7 @@ struct blx_engine {
     float prof_ms[BLX_K_COUNT] = {0};
     int prof_n[BLX_K_COUNT] = {0};
     long long launches = 0;
-    DevBuf scratch_a, scratch_b;
+    DevBuf scratch_a, scratch_b, scratch_near;
 };
 
 static const char *kKernelNames[BLX_K_COUNT] = {"pass1_kernel", "epilogue_kernel", "envelope_kernel", "tail_kernel",
@@ -247,6 +247,7 @@ extern "C" void blx_shutdown(blx_engine *e) {
     }
     e->scratch_a.release();
     e->scratch_b.release();
+    e->scratch_near.release();
     for (auto &r : e->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
     cudaFree(e->d_hann); cudaFree(e->d_tw1f); cudaFree(e->d_tw2f); cudaFree(e->d_tw1d); cudaFree(e->d_tw2d);
@@ -631,8 +632,13 @@ extern "C" int blx_distance_nearest_device(blx_engine *e, const float *d_vectors
     if (rc) return rc;
     if (!d_vectors || n < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n) return fail(BLX_ERR_ARG, "bad distance arguments");
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->compute;
+    // few rows (a rank's slab in a multi-GPU run): the columns are split over gridDim.y and merged through a
+    // per-engine scratch array, so one nearest-neighbour call per engine may be in flight at a time
+    const int splits = distance_nearest_splits(n, n_rows, d_row_sum != nullptr);
+    if (splits > 1) CK(e->scratch_near.reserve((size_t)n_rows * sizeof(unsigned long long)));
     ProfScope ps(e, BLX_K_DISTANCE, st);
-    CK(launch_distance_nearest(d_vectors, n, row0, n_rows, d_nearest_index, d_nearest_dist, d_row_sum, st));
+    CK(launch_distance_nearest(d_vectors, n, row0, n_rows, d_nearest_index, d_nearest_dist, d_row_sum,
+                               static_cast<unsigned long long *>(e->scratch_near.p), splits, st));
     return BLX_OK;
 }
 

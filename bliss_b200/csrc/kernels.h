@@ -59,8 +59,10 @@ cudaError_t launch_logcomp(const double *d_energy, double *d_xlog, long long n, 
 cudaError_t launch_tail(const TailParams &p, int n_songs, cudaStream_t st);
 
 cudaError_t launch_distance_rows(const float *d_vectors, int n, int row0, int n_rows, int mode, float *d_out, cudaStream_t st);
+// splits > 1 (distance_nearest_splits) needs d_packed: n_rows 64-bit words of scratch
+int distance_nearest_splits(int n, int n_rows, bool with_sum);
 cudaError_t launch_distance_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_dist,
-                                    double *d_sum, cudaStream_t st);
+                                    double *d_sum, unsigned long long *d_packed, int splits, cudaStream_t st);
 cudaError_t launch_rect_filter(double *d_out, const double *d_in, int n, int width, cudaStream_t st);
 cudaError_t launch_frontend(const float *d_in, long long n_in, short *d_out, cudaStream_t st);
 

@@ -406,3 +406,33 @@ def test_large_ragged_batch_properties(engine, oracle):
     for i in (0, 7, 19, 48):
         x = base[i]
         check_song(res[first[i]], oracle.analyze(oracle.frontend_f32(x), len(x) // 44100), tag=f"large batch song {i}")
+
+
+def test_distance_nearest_column_splits(engine, oracle):
+    """A slab of few rows against many columns takes the column-split path (gridDim.y > 1, atomicMin merge):
+    same winner as the unsplit scan, including the lowest-index rule for ties across split boundaries."""
+    import torch
+    rng = np.random.default_rng(33)
+    n = 40000
+    v = (rng.standard_normal((n, 4)) * np.array([7, 5, 9, 6])).astype(np.float32)
+    v[123] = v[37000]      # exact collisions far apart (different column ranges)
+    v[30001] = v[5]
+    v[5000] = v[123]       # three-way tie with 37000: row 123 must report the lower index (5000)
+    dv = torch.from_numpy(v).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    rows0, nr = 100, 300   # rows 100..399 only: one row block -> many splits
+    idx = torch.empty(nr, dtype=torch.int32, device="cuda")
+    dist = torch.empty(nr, dtype=torch.float32, device="cuda")
+    engine.distance_nearest_device(dv.data_ptr(), n, rows0, nr, idx.data_ptr(), dist.data_ptr(), 0, stream=st)
+    idx2 = torch.empty(nr, dtype=torch.int32, device="cuda")
+    dist2 = torch.empty(nr, dtype=torch.float32, device="cuda")
+    rsum = torch.empty(nr, dtype=torch.float64, device="cuda")  # asking for row sums forces the unsplit kernel
+    engine.distance_nearest_device(dv.data_ptr(), n, rows0, nr, idx2.data_ptr(), dist2.data_ptr(), rsum.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), idx2.cpu().numpy()) and np.array_equal(dist.cpu().numpy(), dist2.cpu().numpy())
+    got_i, got_d = idx.cpu().numpy(), dist.cpu().numpy()
+    assert got_i[123 - rows0] == 5000 and got_d[123 - rows0] == 0.0
+    for r in (100, 123, 250, 399):
+        d = np.array([oracle.distance(v[r], v[j]) for j in range(n)], dtype=np.float32)
+        d[r] = np.inf
+        assert got_i[r - rows0] == int(np.argmin(d)) and got_d[r - rows0] == d.min(), r
