@@ -124,7 +124,9 @@ int blx_distance_rows_device(blx_engine *e, const float *d_vectors, int n, int r
 /* Fused epilogue for matrices that cannot be materialised (1 M x 1 M): per row of the
  * slab, the nearest other song (ties to the lowest index, as a scan over bl_distance values) and,
  * if d_row_sum is not NULL, the sum of the row's distances (a checksum: float partial sums per
- * 2048-column tile, tiles added in double). Any of the three outputs may be NULL. */
+ * 1024-column tile, tiles added in double). Any of the three outputs may be NULL. A slab with few
+ * rows is computed in column ranges merged through a scratch array owned by the engine: keep one
+ * such call per engine in flight at a time (calls on one stream are ordered anyway). */
 int blx_distance_nearest_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows,
                                 int *d_nearest_index, float *d_nearest_dist, double *d_row_sum, void *stream);
 
