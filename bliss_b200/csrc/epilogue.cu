@@ -27,6 +27,8 @@ namespace blx {
 namespace {
 constexpr int kEpThreads = 256;
 constexpr int kSmW = kHistBins + 6; // 3 zero bins of padding on each side
+constexpr int kEpRun = 15;          // consecutive bins per thread in the smoothing passes (256 x 15 >= 3807)
+static_assert(kEpRun * kEpThreads >= kHistBins, "every bin has an owner");
 
 __device__ __forceinline__ float block_max(float v, float *scratch) {
 #pragma unroll
@@ -42,7 +44,7 @@ __device__ __forceinline__ float block_max(float v, float *scratch) {
 
 __global__ void __launch_bounds__(kEpThreads) epilogue_kernel(EpilogueParams p) {
     __shared__ float ps[257];
-    __shared__ float hA[kSmW], hB[kSmW];
+    __shared__ float hA[kSmW + kEpRun], hB[kSmW + kEpRun]; // + read-ahead of the last owner's window
     __shared__ float scratch[8];
     const int s = blockIdx.x;
     const int tid = threadIdx.x;
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(kEpThreads) epilogue_kernel(EpilogueParams p) 
             // (x + 1 == x from there on).
             const unsigned *gh = p.hist + (size_t)s * kHistStride;
             const unsigned trimmed = (unsigned)first_nz + (unsigned)(sd.n_samples - 1 - last_nz);
-            for (int i = tid; i < kSmW; i += kEpThreads) {
+            for (int i = tid; i < kSmW + kEpRun; i += kEpThreads) {
                 const int b = i - 3;
                 unsigned c = (b >= 0 && b < kHistBins) ? gh[b] : 0u;
                 if (b == 32768 - kHistLo) c -= trimmed;
@@ -100,11 +102,20 @@ __global__ void __launch_bounds__(kEpThreads) epilogue_kernel(EpilogueParams p) 
             }
             __syncthreads();
             float *h = hA, *sm = hB;
+            // every thread owns kEpRun consecutive bins: 21 loads feed its 15 outputs (a sliding window in
+            // registers); a stride of 15 words between threads is bank-conflict free
+            const int i0 = 3 + kEpRun * tid;
             for (int g = 0; g < kSmoothPasses; ++g) {
-                for (int i = 3 + tid; i < 3 + kHistBins; i += kEpThreads) {
-                    const float taps = h[i - 3] + (3 * h[i - 2]) + (6 * h[i - 1]) + (7 * h[i]) + (6 * h[i + 1]) +
-                                       (3 * h[i + 2]) + h[i + 3];
-                    sm[i] = (float)(1. / 27. * (double)taps);
+                if (i0 < 3 + kHistBins) {
+                    float w[kEpRun + 6];
+#pragma unroll
+                    for (int k = 0; k < kEpRun + 6; ++k) w[k] = h[i0 - 3 + k];
+#pragma unroll
+                    for (int k = 0; k < kEpRun; ++k) {
+                        const float taps = w[k] + (3 * w[k + 1]) + (6 * w[k + 2]) + (7 * w[k + 3]) + (6 * w[k + 4]) +
+                                           (3 * w[k + 5]) + w[k + 6];
+                        if (i0 + k < 3 + kHistBins) sm[i0 + k] = (float)(1. / 27. * (double)taps);
+                    }
                 }
                 __syncthreads();
                 float *t = h; h = sm; sm = t; // h now holds this pass's output (reference copies it back)
