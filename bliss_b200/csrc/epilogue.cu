@@ -170,8 +170,21 @@ cudaError_t launch_epilogue(const EpilogueParams &p, int n_songs, cudaStream_t s
 // tail
 // =====================================================================================
 namespace {
-constexpr int kTailThreads = 32;
+constexpr int kTailSongs = 32;   // songs per CTA, one per lane
+constexpr int kTailThreads = 64; // warp 0: a song's owner (everything but the IIR in steady state), warp 1: its IIR
 constexpr int kBox = 19;
+// The IIR recurrence is a 7-operation dependent chain per sample (~92 cycles) and the rest of a sample's work
+// (~45 FP64 operations) does not feed back into it, so in steady state the two run on two warps (two
+// schedulers, two FP64 pipes): warp 1 streams y[n] through a shared-memory ring of kTailBufs blocks of
+// kTailBlk sample pairs, warp 0 consumes them. Named barriers 1.. (full) and 1 + kTailBufs.. (empty).
+constexpr int kTailBlk = 8;      // input pairs (2 samples each) per ring block
+constexpr int kTailBufs = 4;
+
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kTailThreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) {
+    __threadfence_block(); // the ring block / its release is visible before the other warp passes its bar.sync
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(kTailThreads) : "memory");
+}
 
 // reference include/bandpass_coeffs.h:484-492 (data literals)
 __constant__ double c_lp_b[7] = {1.9510e-05, 1.1706e-04, 2.9266e-04, 3.9021e-04, 2.9266e-04, 1.1706e-04, 1.9510e-05};
@@ -207,18 +220,79 @@ struct PeakCounter { // onsets of reference src/tempo_atk_sort.c:277-280, fed on
 } // namespace
 
 __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_songs) {
-    __shared__ double ring1[kBox][kTailThreads]; // last 19 inputs of the first box filter (ss)
-    __shared__ double ring2[kBox][kTailThreads]; // last 19 inputs of the second box filter
-    const int s = blockIdx.x * kTailThreads + threadIdx.x;
-    if (s >= n_songs) return;
-    const int tx = threadIdx.x;
-    const SongDesc sd = p.songs[s];
-    const SongNorm nm = p.norm[s];
+    __shared__ double ring1[kBox][kTailSongs]; // last 19 inputs of the first box filter (ss)
+    __shared__ double ring2[kBox][kTailSongs]; // last 19 inputs of the second box filter
+    __shared__ double ybuf[kTailBufs][2 * kTailBlk][kTailSongs]; // y[n] from the IIR warp to the owner warp
+    __shared__ double hand[9][kTailSongs];     // y1..y6, e1..e3 handed to the IIR warp and back
+    __shared__ int sh_blocks;                  // ring blocks of the piped phase: the same for all songs of the CTA
+    const int tx = threadIdx.x & 31;
+    const int role = threadIdx.x >> 5; // 0 owner, 1 IIR
+    const int s = blockIdx.x * kTailSongs + tx;
+    const bool in_range = s < n_songs;
+    const SongDesc sd = p.songs[in_range ? s : 0];
+    const SongNorm nm = p.norm[in_range ? s : 0];
+    const bool run_env = in_range && (p.what & BLX_DO_ENVELOPE) && nm.status == 0;
+
+    if (role == 1) {
+        // ---- IIR warp: y[n] for the piped phase (reference src/tempo_atk_sort.c:201-218, same operation order)
+        __syncthreads(); // the owners have run their start-up samples and published state + block count
+        const int n_blocks = sh_blocks;
+        const double *X = p.xlog + sd.env_off;
+        double y1 = 0, y2 = 0, y3 = 0, y4 = 0, y5 = 0, y6 = 0, e1 = 0, e2 = 0, e3 = 0;
+        if (run_env) {
+            y1 = hand[0][tx]; y2 = hand[1][tx]; y3 = hand[2][tx]; y4 = hand[3][tx]; y5 = hand[4][tx]; y6 = hand[5][tx];
+            e1 = hand[6][tx]; e2 = hand[7][tx]; e3 = hand[8][tx];
+        }
+        int i = 16; // input index of sample j = 32
+        double cur[kTailBlk];
+#pragma unroll
+        for (int k = 0; k < kTailBlk; ++k) cur[k] = (run_env && n_blocks > 0) ? X[i + k] : 0.0;
+        for (int b = 0; b < n_blocks; ++b) {
+            const int slot = b % kTailBufs;
+            bar_sync(1 + kTailBufs + slot); // the owner has released this ring block
+            if (run_env) {
+                double nxt[kTailBlk]; // next block's inputs: a block is ~1500 cycles of chain, the loads land meanwhile
+#pragma unroll
+                for (int k = 0; k < kTailBlk; ++k) nxt[k] = X[i + kTailBlk + k]; // rows carry 16 doubles of slack
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(X + i + 4 * kTailBlk));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(X + i + 4 * kTailBlk + 4));
+#pragma unroll
+                for (int k = 0; k < kTailBlk; ++k) {
+                    const double e0 = cur[k];
+#pragma unroll
+                    for (int odd = 0; odd < 2; ++odd) {
+                        double d;
+                        if (!odd) { d = c_lp_b[0] * e0; d += c_lp_b[2] * e1; d += c_lp_b[4] * e2; d += c_lp_b[6] * e3; }
+                        else { d = c_lp_b[1] * e0; d += c_lp_b[3] * e1; d += c_lp_b[5] * e2; }
+                        double c = c_lp_a[1] * y1;
+                        c += c_lp_a[2] * y2; c += c_lp_a[3] * y3; c += c_lp_a[4] * y4; c += c_lp_a[5] * y5; c += c_lp_a[6] * y6;
+                        const double y = d - c;
+                        y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
+                        ybuf[slot][2 * k + odd][tx] = y;
+                    }
+                    e3 = e2; e2 = e1; e1 = e0;
+                }
+#pragma unroll
+                for (int k = 0; k < kTailBlk; ++k) cur[k] = nxt[k];
+                i += kTailBlk;
+            }
+            bar_arrive(1 + slot); // block full
+        }
+        if (run_env) {
+            hand[0][tx] = y1; hand[1][tx] = y2; hand[2][tx] = y3; hand[3][tx] = y4; hand[4][tx] = y5; hand[5][tx] = y6;
+            hand[6][tx] = e1; hand[7][tx] = e2; hand[8][tx] = e3;
+        }
+        __syncthreads(); // state handed back
+        return;
+    }
+
     blx_result res;
     res.tempo = 0.0f; res.attack = 0.0f; res.amplitude = nm.amplitude; res.frequency = nm.frequency;
     res.force = 0.0f; res.calm_or_loud = 2; res.beat = 0; res.status = nm.status;
 
-    if ((p.what & BLX_DO_ENVELOPE) && nm.status == 0) {
+    // State of the owner's song lives at function scope: the barrier operations below must run in warp-uniform
+    // control flow, with the per-lane work (lanes without envelope work idle) nested inside.
+    {
         const double *X = p.xlog + sd.env_off; // log(1 + mu E) / log(1 + mu), from logcomp_kernel
         const int nb = 2 * sd.F;
         const int n2 = 2 * nb;
@@ -293,14 +367,12 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
         // branch-free, so everything but the IIR recurrence overlaps it. The x history is zero-stuffed
         // (x1 = x3 = x5 = 0 on even samples, x0 = x2 = x4 = x6 = 0 on odd ones); the skipped products
         // are exact zeros, so the partial sums are the reference's.
-        auto step_steady = [&](double d) {
-            double c = c_lp_a[1] * y1;
-            c += c_lp_a[2] * y2; c += c_lp_a[3] * y3; c += c_lp_a[4] * y4; c += c_lp_a[5] * y5; c += c_lp_a[6] * y6;
-            const double y = d - c;
+        // everything of a steady-state sample but the IIR: y is this sample's filter output, y1 the previous one
+        auto step_rest = [&](double y) {
             double df = y - y1;
             df = (df > 0) ? df : 0;
             const double wa = w_lp * y + div_const<10>(w_df * df);
-            y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
+            y1 = y;
             atk_sum += wa;
             const double o1 = div_const<kBox>(ts1);
             const double s2 = div_const<kBox>(ts2); // out2[p2 - 10]
@@ -314,12 +386,50 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             ring1[r1][tx] = wa;
             r1 = (r1 + 1 == kBox) ? 0 : r1 + 1;
         };
+        auto step_steady = [&](double d) {
+            double c = c_lp_a[1] * y1;
+            c += c_lp_a[2] * y2; c += c_lp_a[3] * y3; c += c_lp_a[4] * y4; c += c_lp_a[5] * y5; c += c_lp_a[6] * y6;
+            const double y = d - c;
+            const double yprev = y1;
+            step_rest(y); // sets y1 = y
+            y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = yprev;
+        };
 
         int j = 0;
-        for (; j < 32; ++j) step_generic(j, (j & 1) ? 0.0 : X[j >> 1]); // n2 >= 40 (BLX_SONG_TOO_SHORT otherwise)
+        if (run_env)
+            for (; j < 32; ++j) step_generic(j, (j & 1) ? 0.0 : X[j >> 1]); // n2 >= 40 (BLX_SONG_TOO_SHORT otherwise)
+        // e1, e2, e3: the three most recent even-index inputs (x at j-2, j-4, j-6 for even j)
+        double e1 = x2, e2 = x4, e3 = x6;
+        // ---- piped phase: whole ring blocks that EVERY song of the CTA still has in its branch-free range
+        // (pairs j, j + 1 with j + 2 <= n2 - 1), the IIR on warp 1
         {
-            // e1, e2, e3: the three most recent even-index inputs (x at j-2, j-4, j-6 for even j)
-            double e1 = x2, e2 = x4, e3 = x6;
+            const int my_blocks = run_env ? ((n2 - 1 - 32) / 2) / kTailBlk : 0x7fffffff;
+            const int nblk = __reduce_min_sync(0xffffffffu, my_blocks);
+            if (tx == 0) sh_blocks = (nblk == 0x7fffffff) ? 0 : nblk;
+            if (run_env) {
+                hand[0][tx] = y1; hand[1][tx] = y2; hand[2][tx] = y3; hand[3][tx] = y4; hand[4][tx] = y5; hand[5][tx] = y6;
+                hand[6][tx] = e1; hand[7][tx] = e2; hand[8][tx] = e3;
+            }
+            __syncthreads();
+            const int n_blocks = sh_blocks;
+            for (int k = 0; k < kTailBufs && k < n_blocks; ++k) bar_arrive(1 + kTailBufs + k); // the ring starts empty
+            for (int b = 0; b < n_blocks; ++b) {
+                const int slot = b % kTailBufs;
+                bar_sync(1 + slot); // block full
+                if (run_env) {
+#pragma unroll 4
+                    for (int k = 0; k < 2 * kTailBlk; ++k) step_rest(ybuf[slot][k][tx]);
+                }
+                if (b + kTailBufs < n_blocks) bar_arrive(1 + kTailBufs + slot); // released (only if it is needed again)
+            }
+            __syncthreads(); // the IIR warp has handed its state back
+            if (run_env && n_blocks > 0) {
+                y1 = hand[0][tx]; y2 = hand[1][tx]; y3 = hand[2][tx]; y4 = hand[3][tx]; y5 = hand[4][tx]; y6 = hand[5][tx];
+                e1 = hand[6][tx]; e2 = hand[7][tx]; e3 = hand[8][tx];
+                j += 2 * kTailBlk * n_blocks;
+            }
+        }
+        if (run_env) {
             int i = j >> 1;
             // one even + one odd sample from the even-index input e0
             auto pair = [&](double e0) {
@@ -357,6 +467,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             // back to the generic history: j is even, x1 = 0, x2 = e1, ...
             x1 = 0; x2 = e1; x3 = 0; x4 = e2; x5 = 0; x6 = e3;
         }
+        if (run_env) {
         for (; j < n2; ++j) step_generic(j, (j & 1) ? 0.0 : X[j >> 1]);
         // ---- end quirks of filter 1 (reference src/tempo_atk_sort.c:34-39): indices n2-10 .. n2-1
         {
@@ -382,9 +493,10 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
         const double atk_score = -1.74 * atk_sum * 10000 / sd.n_samples + 58.3;
         res.tempo = (float)tempo_score;
         res.attack = (float)atk_score;
-    } else if (p.what & BLX_DO_ENVELOPE) {
-        res.tempo = nanf("");
-        res.attack = nanf("");
+        } else if (p.what & BLX_DO_ENVELOPE) {
+            res.tempo = nanf("");
+            res.attack = nanf("");
+        }
     }
 
     if (p.what == BLX_DO_ALL) { // reference src/analyze.c:68-79
@@ -393,7 +505,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
         res.force = rating;
         res.calm_or_loud = (rating > 0) ? 0 : (rating < 0) ? 1 : 2;
     }
-    p.out[s] = res;
+    if (in_range) p.out[s] = res;
 }
 
 // Step 6 of the envelope analyser for every hop of every song at once (reference
@@ -415,7 +527,7 @@ cudaError_t launch_logcomp(const double *d_energy, double *d_xlog, long long n, 
 }
 
 cudaError_t launch_tail(const TailParams &p, int n_songs, cudaStream_t st) {
-    tail_kernel<<<(n_songs + kTailThreads - 1) / kTailThreads, kTailThreads, 0, st>>>(p, n_songs);
+    tail_kernel<<<(n_songs + kTailSongs - 1) / kTailSongs, kTailThreads, 0, st>>>(p, n_songs);
     return cudaGetLastError();
 }
 
