@@ -335,54 +335,79 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant
             constexpr int per_vec = (KIND == kInS16Stereo) ? 4 : 8; // per-channel samples per 16-byte load
             const long long i0 = (long long)tile * kP1Threads * G::elems + (long long)tid * G::elems;
             const int valid_e = (int)max(0ll, min((long long)G::elems, n_elems - i0)); // elements inside the song
-            int row_sum = 0, first_v = 0, last_v = 0;
-            unsigned long long row_sq = 0ull;
+            // as for float input: CHECK = false for a row entirely inside the song, true for the row a song ends in
+            auto do_row = [&](auto check_tag) {
+                constexpr bool CHECK = decltype(check_tag)::value;
+                int row_sum = 0, first_v = 0, last_v = 0;
+                unsigned sq_lo = 0, sq_hi = 0; // 64-bit sum of squares
 #pragma unroll
-            for (int vix = 0; vix < SM::row_bytes / 16; ++vix) {
-                const int4 raw4 = rowp[vix];
-                const int wds[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
-                float o[per_vec];
+                for (int vix = 0; vix < SM::row_bytes / 16; ++vix) {
+                    const int4 raw4 = rowp[vix];
+                    const int wds[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+                    float o[per_vec];
 #pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
-                    const int lo = (int)(short)(wds[wi] & 0xffff);
-                    const int hi = wds[wi] >> 16;
-                    if (KIND == kInS16Stereo) o[wi] = (float)((lo + hi) / 2); // C truncation toward zero
-                    else { o[2 * wi] = (float)lo; o[2 * wi + 1] = (float)hi; }
-                    if (FULL) {
-                        const int e0 = vix * 8 + wi * 2; // element index inside the row
-                        if (e0 < valid_e) { row_sum += lo; row_sq += (unsigned long long)(unsigned)(lo * lo); hist_add(hist, lo, 1u); }
-                        if (e0 + 1 < valid_e) { row_sum += hi; row_sq += (unsigned long long)(unsigned)(hi * hi); hist_add(hist, hi, 1u); }
-                        if (e0 == 0) first_v = lo;
-                        if (e0 + 2 == G::elems) last_v = hi;
+                    for (int wi = 0; wi < 4; ++wi) {
+                        const int lo = (int)(short)(wds[wi] & 0xffff);
+                        const int hi = wds[wi] >> 16;
+                        if (KIND == kInS16Stereo) o[wi] = (float)((lo + hi) / 2); // C truncation toward zero
+                        else { o[2 * wi] = (float)lo; o[2 * wi + 1] = (float)hi; }
+                        if (FULL) {
+                            const int e0 = vix * 8 + wi * 2; // element index inside the row
+                            if (!CHECK) {
+                                row_sum += lo + hi;
+                                const unsigned a = (unsigned)(lo * lo) + (unsigned)(hi * hi); // <= 2^31
+                                sq_lo += a;
+                                sq_hi += (sq_lo < a);
+                                hist_add(hist, lo, 1u);
+                                hist_add(hist, hi, 1u);
+                            } else {
+                                if (e0 < valid_e) {
+                                    row_sum += lo;
+                                    const unsigned a = (unsigned)(lo * lo);
+                                    sq_lo += a; sq_hi += (sq_lo < a);
+                                    hist_add(hist, lo, 1u);
+                                }
+                                if (e0 + 1 < valid_e) {
+                                    row_sum += hi;
+                                    const unsigned a = (unsigned)(hi * hi);
+                                    sq_lo += a; sq_hi += (sq_lo < a);
+                                    hist_add(hist, hi, 1u);
+                                }
+                            }
+                            if (e0 == 0) first_v = lo;
+                            if (e0 + 2 == G::elems) last_v = hi;
+                        }
+                    }
+#pragma unroll
+                    for (int q4 = 0; q4 < per_vec / 4; ++q4) {
+                        const int j = vix * per_vec + q4 * 4;
+                        const float4 hv = *reinterpret_cast<const float4 *>(hrow + j);
+                        float4 r4;
+                        r4.x = o[q4 * 4] * hv.x; r4.y = o[q4 * 4 + 1] * hv.y;
+                        r4.z = o[q4 * 4 + 2] * hv.z; r4.w = o[q4 * 4 + 3] * hv.w;
+                        *reinterpret_cast<float4 *>(fout + j) = r4;
                     }
                 }
-#pragma unroll
-                for (int q4 = 0; q4 < per_vec / 4; ++q4) {
-                    const int j = vix * per_vec + q4 * 4;
-                    const float4 hv = *reinterpret_cast<const float4 *>(hrow + j);
-                    float4 r4;
-                    r4.x = o[q4 * 4] * hv.x; r4.y = o[q4 * 4 + 1] * hv.y;
-                    r4.z = o[q4 * 4 + 2] * hv.z; r4.w = o[q4 * 4 + 3] * hv.w;
-                    *reinterpret_cast<float4 *>(fout + j) = r4;
+                if (FULL && valid_e > 0) {
+                    ts.sum += row_sum;
+                    ts.sumsq += ((unsigned long long)sq_hi << 32) | sq_lo;
+                    // first / last non-zero sample: the row's end samples decide unless one of them is zero
+                    // or the row is cut by the song's end (then scan the row)
+                    if (!CHECK && first_v != 0 && last_v != 0) {
+                        ts.first_nz = min(ts.first_nz, (int)i0);
+                        ts.last_nz = max(ts.last_nz, (int)i0 + G::elems - 1);
+                    } else {
+                        const short *rs = reinterpret_cast<const short *>(rowp);
+                        for (int i = 0; i < valid_e; ++i)
+                            if (rs[i] != 0) {
+                                ts.first_nz = min(ts.first_nz, (int)i0 + i);
+                                ts.last_nz = max(ts.last_nz, (int)i0 + i);
+                            }
+                    }
                 }
-            }
-            if (FULL && valid_e > 0) {
-                ts.sum += row_sum;
-                ts.sumsq += row_sq;
-                // first / last non-zero sample: the row's end samples decide unless one of them is zero
-                // or the row is cut by the song's end (then scan the row)
-                if (valid_e == G::elems && first_v != 0 && last_v != 0) {
-                    ts.first_nz = min(ts.first_nz, (int)i0);
-                    ts.last_nz = max(ts.last_nz, (int)i0 + G::elems - 1);
-                } else {
-                    const short *rs = reinterpret_cast<const short *>(rowp);
-                    for (int i = 0; i < valid_e; ++i)
-                        if (rs[i] != 0) {
-                            ts.first_nz = min(ts.first_nz, (int)i0 + i);
-                            ts.last_nz = max(ts.last_nz, (int)i0 + i);
-                        }
-                }
-            }
+            };
+            if (!FULL || valid_e == G::elems) do_row(std::false_type{});
+            else do_row(std::true_type{});
         }
         __syncthreads(); // rows consumed, fin complete
 
