@@ -26,15 +26,18 @@
 //
 // The float accumulation s <- (float)((double)s + p_k), k = 0..256, is a chain of 257 dependent
 // roundings (~50-75 cycles each on the FP64 + conversion pipes): run naively it idles the SM. It is
-// evaluated here by the 16 lanes that hold the hop's spectrum, as a SCAN:
+// evaluated by the 16 lanes that hold the hop's spectrum:
 //   while s stays inside one binade [2^e, 2^(e+1)) its float grid is g = 2^(e-23) and
 //   RN_g(s + p) = s + RN_g(p) because s is a multiple of g; so with q = s / g (a 24-bit integer)
 //   the chain is q += I_k with I_k = RN_g(p_k) / g, which one double addition p_k + 1.5 * 2^52 * g
-//   leaves in the low mantissa word. Each lane converts its 16 bins, an integer prefix scan over the
-//   half-warp gives every partial sum at once, and the first bin k* at which q + prefix reaches 2^24
-//   (the sum leaves the binade) is found with a ballot. Bins below k* are final; bin k* is added with
-//   the reference's own double-add / float-convert sequence, which yields the next binade, and the
-//   scan restarts after k*. A hop needs one round per binade crossing (typically 2-6).
+//   leaves in the low mantissa word.
+// float_chain (below) predicts the binade of every bin from an exact double prefix scan of the
+// spectrum, converts every bin once at its predicted grid, takes the few binade crossings in order
+// through the reference's own double-add / float-convert step, and verifies every prediction on
+// the way; the rare hop that fails is redone by float_chain_rounds / chain_round, the first form of
+// the algorithm: one prefix-scan round per binade (every lane converts its 16 bins at the current
+// grid, the first bin k* at which q + prefix reaches 2^24 is found with a ballot, bin k* is added
+// with the reference step, the scan restarts after k*).
 // The result equals the reference's chain except when s + p_k lies within 2^-29 grid units of a
 // rounding midpoint (the reference rounds to double, then to float; exact ties follow the parity of
 // the magic constant instead of q).
