@@ -108,6 +108,20 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// ---------------------------------------------------------------- host: once-per-device set-up
+// cudaFuncSetAttribute applies to the current device only; a process may run one engine per GPU.
+struct PerDeviceOnce {
+    bool done[64] = {false};
+    // true if `fn` still has to run for the current device (and marks it as run)
+    bool first_time() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ double int_to_double_exact(int v) {
     // 2^52 + 2^31 + v is exactly representable; one integer op + one DADD instead of I2F.F64

@@ -614,13 +614,12 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
 }
 
 cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first_time()) {
         cudaError_t e = cudaFuncSetAttribute(envelope_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<true>::bytes);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(envelope_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<false>::bytes);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     if (max_hops <= 0) return cudaSuccess;
     dim3 grid((unsigned)((max_hops + kHopsPerCta - 1) / kHopsPerCta), (unsigned)n_songs);

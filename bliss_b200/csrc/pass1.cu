@@ -534,11 +534,10 @@ cudaError_t make_pass1_maps(Pass1Params *p, const void *d_pcm, long long rows) {
 template <int KIND, bool FULL> static cudaError_t launch_one(const Pass1Params &p, int max_parts, int n_songs, cudaStream_t st) {
     using SM = P1Smem<KIND>;
     const int bytes = FULL ? SM::bytes_full : SM::bytes_lite;
-    static bool configured = false;
-    if (!configured) { // one process drives one device (one rank per GPU)
+    static PerDeviceOnce once;
+    if (once.first_time()) {
         cudaError_t e = cudaFuncSetAttribute(pass1_kernel<KIND, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     dim3 grid((unsigned)max_parts, (unsigned)n_songs);
     pass1_kernel<KIND, FULL><<<grid, kP1Threads, bytes, st>>>(p);
