@@ -54,7 +54,7 @@ namespace blx {
 namespace {
 constexpr int kEnvThreads = 256;                 // 8 independent warps
 constexpr int kEnvWarps = kEnvThreads / 32;
-constexpr int kPairsPerWarp = 16;                // a warp owns 32 consecutive hops
+constexpr int kPairsPerWarp = 32;                // a warp owns 64 consecutive hops
 constexpr int kHopsPerCta = 2 * kPairsPerWarp * kEnvWarps;
 constexpr int kSlotBytes = kHop * 8;             // one block of 256 FIR outputs (128 cells of 16 bytes)
 

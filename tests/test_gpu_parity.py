@@ -332,9 +332,9 @@ def test_envelope_fast_chain_equals_slow_chain(engine):
 
 
 def test_envelope_hop_counts_around_warp_and_cta_boundaries(engine, oracle):
-    """A warp owns 32 hops and a CTA 256 (n_hops = 2 F - 2 is always even): songs whose hop count ends
-    just before / on / after those boundaries."""
-    for n_hops in (18, 30, 32, 34, 62, 64, 66, 254, 256, 258, 290):
+    """A warp owns a run of consecutive hops (a power of two, 32..128) and a CTA eight of them (n_hops = 2 F - 2
+    is always even): songs whose hop count ends just before / on / after those boundaries."""
+    for n_hops in (18, 30, 32, 34, 62, 64, 66, 126, 128, 130, 254, 256, 258, 510, 512, 514, 1022, 1024, 1026, 1090):
         F = (n_hops + 2) // 2
         pcm = np.resize(song_s16(500 + n_hops, 1.0, decorrelate=True), 512 * F + 37)
         E, Eo = engine.envelope_energy(pcm), oracle.envelope_energy(pcm)
