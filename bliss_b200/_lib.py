@@ -59,6 +59,7 @@ BLX_H_SYMBOLS = [
     "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_device", "blx_spectral_device",
     "blx_distance_matrix", "blx_cosine_matrix", "blx_distance_rows_device", "blx_distance_nearest_device",
     "blx_mean_variance_s16", "blx_rectangular_filter", "blx_frontend_f32", "blx_envelope_energy_s16",
+    "blx_frequency_spectrum_s16", "blx_histogram_s16", "blx_envelope_tail",
     "blx_profile_enable", "blx_profile_reset", "blx_profile_read", "blx_kernel_name", "blx_launch_count",
 ]
 
@@ -113,6 +114,12 @@ def load():
     L.blx_frontend_f32.argtypes = [vp, c_f32p, ctypes.c_int64, c_i16p]
     L.blx_envelope_energy_s16.restype = ctypes.c_int
     L.blx_envelope_energy_s16.argtypes = [vp, c_i16p, ctypes.c_int, c_f64p]
+    L.blx_frequency_spectrum_s16.restype = ctypes.c_int
+    L.blx_frequency_spectrum_s16.argtypes = [vp, c_i16p, ctypes.c_int, ctypes.c_int, c_f32p]
+    L.blx_histogram_s16.restype = ctypes.c_int
+    L.blx_histogram_s16.argtypes = [vp, c_i16p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint), c_i32p, c_i32p]
+    L.blx_envelope_tail.restype = ctypes.c_int
+    L.blx_envelope_tail.argtypes = [vp, c_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, c_i32p, c_f32p, c_f32p]
     L.blx_profile_enable.restype = ctypes.c_int
     L.blx_profile_enable.argtypes = [vp, ctypes.c_int]
     L.blx_profile_reset.restype = ctypes.c_int

@@ -1,7 +1,7 @@
 // engine.cu — the C-ABI of blx.h: device memory, streams, batching and kernel sequencing.
 //
 // Per chunk of songs the engine enqueues
-//     memset(hist, stats, energy) -> pass1 -> epilogue -> envelope -> tail
+//     memset(hist, stats) -> pass1 -> epilogue -> envelope -> logcomp -> tail
 // on one stream. The host-buffer entry points split a batch into chunks that fit a device
 // staging buffer and alternate between two slots, so the host->device copy of chunk i+1
 // (copy stream) overlaps the kernels of chunk i (compute stream).
@@ -375,7 +375,6 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
     if (full) {
         CK(cudaMemsetAsync(s.hist.p, 0, (size_t)n * kHistStride * sizeof(unsigned), st));
         CK(cudaMemsetAsync(s.stats.p, 0, (size_t)n * sizeof(SongStats), st));
-        if (what & BLX_DO_ENVELOPE) CK(cudaMemsetAsync(s.energy.p, 0, (size_t)plan.energy_total * sizeof(double), st));
     }
     const SongDesc *d_songs = static_cast<const SongDesc *>(s.songs.p);
     {
@@ -403,6 +402,7 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         p.stats = full ? static_cast<const SongStats *>(s.stats.p) : nullptr;
         p.norm = static_cast<SongNorm *>(s.norm.p);
         p.frequency = d_freq_only;
+        p.energy = (full && (what & BLX_DO_ENVELOPE)) ? static_cast<double *>(s.energy.p) : nullptr;
         p.what = full ? what : BLX_DO_FREQUENCY;
         ProfScope ps(e, BLX_K_EPILOGUE, st);
         CK(launch_epilogue(p, n, st));
@@ -738,5 +738,94 @@ extern "C" int blx_envelope_energy_s16(blx_engine *e, const int16_t *pcm, int n_
     if (rc) return rc;
     const int nb = 2 * (n_samples / kWin);
     if (nb > 0) CK(cudaMemcpy(energy, e->slot[0].energy.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost));
+    return BLX_OK;
+}
+
+// ---------------------------------------------------------------- stage-level views (kernel parity tests)
+extern "C" int blx_frequency_spectrum_s16(blx_engine *e, const int16_t *pcm, int n_samples, int channels, float *ps) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!pcm || n_samples <= 0 || !ps || (channels != 1 && channels != 2)) return fail(BLX_ERR_ARG, "bad arguments");
+    const int16_t *ptrs[1] = {pcm};
+    const int ns[1] = {n_samples}, ch[1] = {channels};
+    const uint64_t du[1] = {1};
+    blx_result r;
+    e->next_slot = 0;
+    rc = blx_analyze_batch_s16(e, ptrs, ns, ch, du, 1, BLX_DO_FREQUENCY | BLX_DO_AMPLITUDE, &r);
+    if (rc) return rc;
+    const int n_parts = e->slot[0].h_songs[0].n_parts;
+    std::vector<float> part((size_t)n_parts * 256);
+    CK(cudaMemcpy(part.data(), e->slot[0].partials.p, part.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    // the epilogue kernel's own order: parts added one after the other, in float
+    for (int d = 0; d <= 256; ++d) ps[d] = 0.0f;
+    for (int d = 1; d < 256; ++d) {
+        float acc = 0.0f;
+        for (int q = 0; q < n_parts; ++q) acc += part[(size_t)q * 256 + d];
+        ps[d] = acc;
+    }
+    return BLX_OK;
+}
+
+extern "C" int blx_histogram_s16(blx_engine *e, const int16_t *pcm, int n_samples, unsigned *hist, int *first_nonzero,
+                                 int *last_nonzero) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!pcm || n_samples <= 0 || !hist) return fail(BLX_ERR_ARG, "bad arguments");
+    blx_result r;
+    rc = one_song_s16(e, pcm, n_samples, 1, BLX_DO_AMPLITUDE, &r);
+    if (rc) return rc;
+    SongStats st;
+    CK(cudaMemcpy(hist, e->slot[0].hist.p, (size_t)kHistBins * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, e->slot[0].stats.p, sizeof(st), cudaMemcpyDeviceToHost));
+    if (first_nonzero) *first_nonzero = st.last_p1 ? (int)(0x7fffffffu - st.first_inv) : -1;
+    if (last_nonzero) *last_nonzero = (int)st.last_p1 - 1;
+    return BLX_OK;
+}
+
+extern "C" int blx_envelope_tail(blx_engine *e, const double *energy, int nb_frames, int n_samples, uint64_t duration_s,
+                                 int *beat, float *tempo, float *attack) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!energy || nb_frames < 10 || (nb_frames & 1) || n_samples <= 0 || duration_s == 0)
+        return fail(BLX_ERR_ARG, "bad arguments (nb_frames = 2 * (n_samples / 512) >= 10, duration >= 1)");
+    Slot &s = e->slot[0];
+    if (s.busy) { CK(cudaEventSynchronize(s.done)); s.busy = false; }
+    rc = ensure_host_songs(s, 1);
+    if (rc) return rc;
+    SongDesc d;
+    memset(&d, 0, sizeof(d));
+    d.n_samples = n_samples;
+    d.F = nb_frames / 2;
+    d.n_hops = nb_frames - 2;
+    d.duration = (unsigned)duration_s;
+    s.h_songs[0] = d;
+    SongNorm nm;
+    memset(&nm, 0, sizeof(nm));
+    const size_t row = (size_t)round_up(nb_frames, 8);
+    CK(s.songs.reserve(sizeof(SongDesc)));
+    CK(s.norm.reserve(sizeof(SongNorm)));
+    CK(s.energy.reserve(row * sizeof(double)));
+    CK(s.xlog.reserve((row + 16) * sizeof(double)));
+    CK(s.results.reserve(sizeof(blx_result)));
+    cudaStream_t st = e->compute;
+    CK(cudaMemcpyAsync(s.songs.p, s.h_songs, sizeof(SongDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.norm.p, &nm, sizeof(nm), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(s.energy.p, 0, row * sizeof(double), st));
+    CK(cudaMemcpyAsync(s.energy.p, energy, (size_t)nb_frames * sizeof(double), cudaMemcpyHostToDevice, st));
+    e->launches += 2;
+    CK(launch_logcomp(static_cast<const double *>(s.energy.p), static_cast<double *>(s.xlog.p), (long long)row, st));
+    TailParams p;
+    p.songs = static_cast<const SongDesc *>(s.songs.p);
+    p.norm = static_cast<const SongNorm *>(s.norm.p);
+    p.xlog = static_cast<const double *>(s.xlog.p);
+    p.out = static_cast<blx_result *>(s.results.p);
+    p.what = BLX_DO_ENVELOPE;
+    CK(launch_tail(p, 1, st));
+    blx_result r;
+    CK(cudaMemcpyAsync(&r, s.results.p, sizeof(r), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (beat) *beat = r.beat;
+    if (tempo) *tempo = r.tempo;
+    if (attack) *attack = r.attack;
     return BLX_OK;
 }

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kEpThreads) epilogue_kernel(EpilogueParams p) 
     __shared__ float ps[257];
     __shared__ float hA[kSmW + kEpRun], hB[kSmW + kEpRun]; // + read-ahead of the last owner's window
     __shared__ float scratch[8];
+    __shared__ int sh_status;
     const int s = blockIdx.x;
     const int tid = threadIdx.x;
     const SongDesc sd = p.songs[s];
@@ -158,6 +159,15 @@ __global__ void __launch_bounds__(kEpThreads) epilogue_kernel(EpilogueParams p) 
         }
         p.norm[s] = out;
         if (p.frequency) p.frequency[s] = out.frequency;
+        sh_status = out.status;
+    }
+    // E[M], E[M + 1] stay 0 in the reference (calloc, reference src/tempo_atk_sort.c:84): the envelope kernel
+    // writes hops 0..M-1 only. A song it skips (status != 0) gets a cleared row.
+    if (p.energy && (p.what & BLX_DO_ENVELOPE)) {
+        __syncthreads();
+        double *row = p.energy + sd.env_off;
+        const int nb = 2 * sd.F;
+        for (int i = (sh_status ? 0 : max(sd.n_hops, 0)) + tid; i < nb; i += kEpThreads) row[i] = 0.0;
     }
 }
 

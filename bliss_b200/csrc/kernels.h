@@ -32,6 +32,7 @@ struct EpilogueParams {
     const SongStats *stats;
     SongNorm *norm;     // out
     float *frequency;   // optional out (spectral-only entry point), may be NULL
+    double *energy;     // envelope rows (SongDesc::env_off): entries past the last hop are cleared here; may be NULL
     unsigned what;      // BLX_DO_* mask
 };
 cudaError_t launch_epilogue(const EpilogueParams &p, int n_songs, cudaStream_t st);

@@ -163,6 +163,32 @@ class Engine:
         self._ck(self._lib.blx_envelope_energy_s16(self._h, a.ctypes.data_as(L.c_i16p), len(a), E.ctypes.data_as(L.c_f64p)))
         return E[:nb]
 
+    def frequency_spectrum(self, pcm, channels=2):
+        """Per-bin power (sum over frames of |X_d|^2, d = 1..255) before the scalar epilogue; 257 floats."""
+        a = np.ascontiguousarray(pcm, dtype=np.int16)
+        ps = np.zeros(257, dtype=np.float32)
+        self._ck(self._lib.blx_frequency_spectrum_s16(self._h, a.ctypes.data_as(L.c_i16p), len(a), int(channels),
+                                                      ps.ctypes.data_as(L.c_f32p)))
+        return ps
+
+    def histogram(self, pcm):
+        """(counts of sample values -1904..+1902, first non-zero index, last non-zero index)."""
+        a = np.ascontiguousarray(pcm, dtype=np.int16)
+        h = np.zeros(3807, dtype=np.uint32)
+        first, last = ctypes.c_int(0), ctypes.c_int(0)
+        self._ck(self._lib.blx_histogram_s16(self._h, a.ctypes.data_as(L.c_i16p), len(a),
+                                             h.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.byref(first),
+                                             ctypes.byref(last)))
+        return h, first.value, last.value
+
+    def envelope_tail(self, energy, n_samples, duration):
+        """The sequential tail alone on given hop energies: dict(beat, tempo, attack)."""
+        E = np.ascontiguousarray(energy, dtype=np.float64)
+        beat, tempo, attack = ctypes.c_int(0), ctypes.c_float(0), ctypes.c_float(0)
+        self._ck(self._lib.blx_envelope_tail(self._h, E.ctypes.data_as(L.c_f64p), len(E), int(n_samples), int(duration),
+                                             ctypes.byref(beat), ctypes.byref(tempo), ctypes.byref(attack)))
+        return dict(beat=beat.value, tempo=tempo.value, attack=attack.value)
+
     def debug_flags(self, flags):
         """Test hooks (include/blx.h BLX_DEBUG_*); results must not depend on them."""
         self._ck(self._lib.blx_debug_flags(self._h, int(flags)))

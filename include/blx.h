@@ -148,6 +148,22 @@ int blx_frontend_f32(blx_engine *e, const float *pcm, int64_t n_in, int16_t *out
  * (reference src/tempo_atk_sort.c:150), 2 * (n_samples / 512) doubles, host. */
 int blx_envelope_energy_s16(blx_engine *e, const int16_t *pcm, int n_samples, double *energy);
 
+/* Per-bin power spectrum of the frequency analyser BEFORE its scalar epilogue: ps[d] = sum over frames
+ * of |X_d|^2, d = 1..255 (reference src/frequency_sort.c:88-93); ps[0] = ps[256] = 0. 257 floats, host. */
+int blx_frequency_spectrum_s16(blx_engine *e, const int16_t *pcm, int n_samples, int channels, float *ps);
+
+/* The amplitude analyser's sample histogram as pass 1 counts it: bins for sample values -1904..+1902
+ * (3807 counters, value v at index v + 1904), over ALL samples; first/last_nonzero = the bounds of
+ * reference src/amplitude_sort.c:26-31 (-1 for an all-zero song). */
+int blx_histogram_s16(blx_engine *e, const int16_t *pcm, int n_samples, unsigned *hist /* [3807] */,
+                      int *first_nonzero, int *last_nonzero);
+
+/* The envelope analyser's sequential tail ALONE on caller-supplied hop energies (reference
+ * src/tempo_atk_sort.c:184-287: log compression, IIR, rectified difference, mix, two box filters, onset
+ * count, scores). energy: nb_frames = 2 * (n_samples / 512) doubles (the last two 0), host. */
+int blx_envelope_tail(blx_engine *e, const double *energy, int nb_frames, int n_samples, uint64_t duration_s,
+                      int *beat, float *tempo, float *attack);
+
 /* ---- measurement ------------------------------------------------------------------
  * With profiling on, every kernel launch is bracketed by CUDA events on its own stream.
  * blx_profile_read synchronises and returns, per kernel id, the accumulated device time

@@ -436,3 +436,88 @@ def test_distance_nearest_column_splits(engine, oracle):
         d = np.array([oracle.distance(v[r], v[j]) for j in range(n)], dtype=np.float32)
         d[r] = np.inf
         assert got_i[r - rows0] == int(np.argmin(d)) and got_d[r - rows0] == d.min(), r
+
+
+# ---------------------------------------------------------------- stage-level parity (one kernel at a time)
+def test_stage_frequency_spectrum_per_bin(engine, oracle):
+    """pass 1 alone: the per-bin power sum_f |X_d|^2 (before the dB compression of the rating hides per-bin
+    errors) against the oracle's double FFT rounded to float (reference src/frequency_sort.c:83-93), for
+    stereo (decorrelated channels), mono, and a float32 song after the front-end."""
+    cases = [(song_s16(61, 12.0, decorrelate=True), 2), (song_s16(62, 4.0, gain=0.2), 2), (song_s16(63, 7.0)[::2].copy(), 1),
+             (oracle.frontend_f32(song_f32(64, 9.0)), 2), (_tonal_song(5, 5.0, 2500.0, 3.0), 2)]
+    worst = 0.0
+    for i, (pcm, ch) in enumerate(cases):
+        ps, ref = engine.frequency_spectrum(pcm, ch), oracle.frequency_spectrum(pcm, ch)
+        assert ps[0] == 0 and ps[256] == 0
+        err = np.abs(ps[1:256].astype(np.float64) - ref[1:256]) / (ref[1:256] + 1e-7 * ref[1:256].max())
+        worst = max(worst, float(err.max()))
+        assert err.max() <= 2e-5, (i, int(err.argmax()) + 1, float(err.max()))
+        # the scalar epilogue of the rating is the oracle's on the same spectrum
+        f_gpu = float(engine.analyze_s16([pcm], [max(1, len(pcm) // (22050 * ch))], channels=[ch], what=bliss_b200.DO_FREQUENCY)[0]["frequency"])
+        assert rel(f_gpu, oracle.frequency_from_spectrum(ps)) <= 1e-6, i
+    print(f"per-bin spectrum: worst relative error {worst:.3g}")
+
+
+def test_stage_histogram_and_bounds(engine):
+    """pass 1's integer side products: the exact histogram of the 3 807 relevant sample values and the
+    first / last non-zero sample (reference src/amplitude_sort.c:26-39), against numpy."""
+    pcm = song_s16(65, 6.0, decorrelate=True, gain=0.03)
+    pcm[:1234] = 0
+    pcm[-77:] = 0
+    h, first, last = engine.histogram(pcm)
+    want = np.bincount(pcm.astype(np.int64) + 32768, minlength=65536)[30864:34671]
+    nz = np.flatnonzero(pcm)
+    assert np.array_equal(h, want) and first == nz[0] and last == nz[-1]
+    loud = song_s16(66, 3.0, gain=1.9)  # most samples outside the window: predicated atomics
+    h2, _, _ = engine.histogram(loud)
+    assert np.array_equal(h2, np.bincount(loud.astype(np.int64) + 32768, minlength=65536)[30864:34671])
+
+
+def test_stage_envelope_tail_on_oracle_energies(engine, oracle):
+    """logcomp + tail kernels alone, fed the ORACLE's hop energies: onset count and tempo exact, attack to
+    float rounding (device log() vs glibc's), against orc_envelope_tail (reference
+    src/tempo_atk_sort.c:184-287) - independent of the envelope kernel's FFT."""
+    for i, (pcm, dur) in enumerate([(song_s16(67, 14.0, decorrelate=True), 14), (song_s16(68, 2.0), 2),
+                                    (_tonal_song(6, 8.0, 700.0, 5.0), 8), (song_s16(69, 61.0, gain=0.3), 61)]):
+        E = oracle.envelope_energy(pcm)
+        ref = oracle.envelope_tail(E, len(pcm), dur)
+        got = engine.envelope_tail(E, len(pcm), dur)
+        assert got["beat"] == ref["beat"], (i, got, ref)
+        assert got["tempo"] == ref["tempo"], (i, got, ref)
+        assert rel(got["attack"], ref["attack"]) <= 1e-6, (i, got, ref)
+    # a synthetic envelope with exact ties and plateaus (differences of exactly 0 and exactly epsilon-scale)
+    E = np.zeros(400)
+    E[10:390:20] = 3.0
+    E[15:390:20] = 3.0
+    E[-2:] = 0
+    ref = oracle.envelope_tail(E, 200 * 512 + 5, 4)
+    got = engine.envelope_tail(E, 200 * 512 + 5, 4)
+    assert got["beat"] == ref["beat"] and got["tempo"] == ref["tempo"] and rel(got["attack"], ref["attack"]) <= 1e-6
+
+
+def test_bl_distance_file_two_different_files(engine, oracle, tmp_path):
+    """reference src/analyze.c:105-125 on two DIFFERENT files: the distance equals bl_distance of the two
+    analysed vectors bit for bit, and of the oracle's vectors for the same PCM to 1e-4."""
+    import wave
+    L = bliss_b200.load()
+    pcm = song_s16(70, 9.0, decorrelate=True, gain=0.6)
+    wav = str(tmp_path / "other.wav")
+    with wave.open(wav, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(22050)
+        w.writeframes(pcm.tobytes())
+    flac = os.path.join(GOLDEN_DIR, "song.flac").encode()
+    s1, s2 = bliss_b200.BlSong(), bliss_b200.BlSong()
+    d = L.bl_distance_file(flac, wav.encode(), ctypes.byref(s1), ctypes.byref(s2))
+    v1 = [s1.force_vector.tempo, s1.force_vector.amplitude, s1.force_vector.frequency, s1.force_vector.attack]
+    v2 = [s2.force_vector.tempo, s2.force_vector.amplitude, s2.force_vector.frequency, s2.force_vector.attack]
+    assert d > 1.0 and d == np.float32(oracle.distance(v1, v2))
+    assert d == L.bl_distance(s1.force_vector, s2.force_vector)
+    c = L.bl_cosine_similarity_file(flac, wav.encode(), ctypes.byref(s1), ctypes.byref(s2))
+    assert c == np.float32(oracle.cosine_similarity(v1, v2)) and -1.0 <= c < 1.0
+    ref2 = oracle.analyze(pcm, 9)
+    from test_oracle import GOLDEN_S16
+    o1 = [GOLDEN_S16[k] for k in ("tempo", "amplitude", "frequency", "attack")]
+    o2 = [ref2[k] for k in ("tempo", "amplitude", "frequency", "attack")]
+    assert rel(d, oracle.distance(o1, o2)) <= 1e-4
+    assert s2.nSamples == len(pcm) and s2.duration == 9
+    L.bl_free_song(ctypes.byref(s1)); L.bl_free_song(ctypes.byref(s2))
