@@ -116,33 +116,50 @@ def _cpu_analyze(i):
     return (i, r["tempo"], r["amplitude"], r["frequency"], r["attack"])
 
 
-def cpu_leg(f32, steps, warmup, workers=None):
-    """Times the reference's CPU analysers on the songs of `f32` (S x n float32, 44.1 kHz mono).
-    The f32 -> int16/22 050 Hz/stereo front-end (oracle/frontend.c, the same arithmetic the GPU fuses
+def _cpu_energy(i):
+    from oracle.binding import Oracle
+    orc = _CPU.setdefault("orc", Oracle())
+    return (i, orc.envelope_energy(_CPU["s16"][i]))
+
+
+def cpu_leg(pcm, steps, warmup, workers=None, energies=0, energy_path=None):
+    """Times the reference's CPU analysers on the songs of `pcm`: S x n float32 (44.1 kHz mono) or S x n int16
+    (22 050 Hz stereo interleaved, the analysers' native input).
+    For float32 the f32 -> int16/22 050 Hz/stereo front-end (oracle/frontend.c, the same arithmetic the GPU fuses
     into pass 1) runs first and is NOT timed: decode/resample is excluded on both sides.
-    Worker PROCESSES, one per core: the reference is not thread-safe (fftw planner)."""
+    Worker PROCESSES, one per core: the reference is not thread-safe (fftw planner).
+    energies = K > 0: also writes the hop energies E[m] (oracle restatement) of the first K songs to energy_path."""
     import multiprocessing as mp
 
     from oracle.binding import REF_SO
-    S, n = f32.shape
+    S, n = pcm.shape
     cores = os.cpu_count() or 1
     workers = max(1, min(workers or cores, S))
-    n16 = 2 * (n // 2)
-    shm = mmap.mmap(-1, S * n16 * 2)
-    _CPU["f32"] = f32
-    _CPU["s16"] = np.frombuffer(shm, dtype=np.int16).reshape(S, n16)
+    is_f32 = pcm.dtype == np.float32
+    n16 = 2 * (n // 2) if is_f32 else n
+    if is_f32:
+        shm = mmap.mmap(-1, S * n16 * 2)
+        _CPU["f32"] = pcm
+        _CPU["s16"] = np.frombuffer(shm, dtype=np.int16).reshape(S, n16)
+        _CPU["duration"] = n // RATE_IN
+    else:
+        _CPU["s16"] = pcm
+        _CPU["duration"] = n // RATE_IN  # n int16 values = n / 2 frames at 22 050 Hz
     _CPU["kind"] = "reference" if os.path.exists(REF_SO) else "port"
-    _CPU["duration"] = n // RATE_IN
     ctx = mp.get_context("fork")
     times, results = [], None
     with ctx.Pool(workers) as pool:
-        pool.map(_cpu_frontend, range(S), chunksize=1)
+        if is_f32:
+            pool.map(_cpu_frontend, range(S), chunksize=1)
         for it in range(warmup + steps):
             t0 = time.perf_counter()
             results = pool.map(_cpu_analyze, range(S), chunksize=1)
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
+        if energies > 0 and energy_path:
+            en = pool.map(_cpu_energy, range(min(energies, S)), chunksize=1)
+            np.save(energy_path, np.stack([e for _, e in sorted(en, key=lambda t: t[0])]))
     total = sum(times)
     res = np.zeros((S, 4), dtype=np.float64)
     for i, a, b, c, d in results:
@@ -151,14 +168,18 @@ def cpu_leg(f32, steps, warmup, workers=None):
                 kind=_CPU["kind"], songs=S, results=res.tolist())
 
 
-def cpu_leg_subprocess(f32, steps, warmup):
-    """Runs cpu_leg in a fresh interpreter (no CUDA context to fork)."""
+def cpu_leg_subprocess(pcm, steps, warmup, energies=0):
+    """Runs cpu_leg in a fresh interpreter (no CUDA context to fork). Returns (leg dict, energies or None)."""
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
         path = os.path.join(d, "sample.npy")
-        np.save(path, f32)
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--_cpu-leg", path, "--steps", str(steps),
-                              "--warmup", str(warmup)], check=True, capture_output=True, text=True)
-    return json.loads(out.stdout.strip().splitlines()[-1])
+        epath = os.path.join(d, "energy.npy")
+        np.save(path, pcm)
+        cmd = [sys.executable, os.path.abspath(__file__), "--_cpu-leg", path, "--steps", str(steps), "--warmup", str(warmup)]
+        if energies:
+            cmd += ["--_cpu-energies", str(energies), "--_cpu-energy-path", epath]
+        out = subprocess.run(cmd, check=True, capture_output=True, text=True)
+        E = np.load(epath) if energies else None
+    return json.loads(out.stdout.strip().splitlines()[-1]), E
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -249,6 +270,212 @@ def workload_config(args, songs_per_step, n_gpus):
     }
 
 
+# ------------------------------------------------------------------------------------------ parity campaign
+def make_s16_stereo(torch, left_f32, right_f32):
+    """int16 / 22 050 Hz / stereo interleaved from two 44.1 kHz float32 songs: L = every other sample of the
+    first, R = a mix of both (decorrelated channels, the reference decoder's usual output)."""
+    L = torch.clamp(torch.round(left_f32[::2] * 32768.0), -32768, 32767)
+    R = torch.clamp(torch.round((0.6 * left_f32[::2] + 0.4 * right_f32[::2]) * 32768.0), -32768, 32767)
+    return torch.stack([L, R], dim=1).reshape(-1).to(torch.int16)
+
+
+def parity_campaign(torch, eng, E, dev, stream, rank, world, total, dist):
+    """GPU records against the CPU analysers (oracle/_ref when built, else the oracle port) over `total` songs
+    shared by all ranks: 30-s and 3-minute songs, float32 (front-end + doubled-mono kernels) AND native int16
+    stereo with decorrelated channels (the reference's real input). Reports onset-count mismatches (must be 0),
+    the largest relative error per component and the measured rate of single-ulp flips of E[m]."""
+    import bliss_b200
+    per_rank = -(-total // world)
+    n_long = max(2, per_rank // 32)  # 3-minute songs of each format
+    n_short = max(2, (per_rank - 2 * n_long + 1) // 2)
+    groups = [("f32_30s", "f32", 30, n_short, 256), ("s16_30s", "s16", 30, n_short, 256),
+              ("f32_180s", "f32", 180, n_long, 32), ("s16_180s", "s16", 180, n_long, 32)]
+    comps = ("tempo", "amplitude", "frequency", "attack")
+    max_rel = {k: 0.0 for k in comps}
+    beat_mismatch, status_bad, n_done, cpu_s = 0, 0, 0, 0.0
+    flips, hops, e_max_rel = 0, 0, 0.0
+    per_group = {}
+    kind = None
+    base_index = 1_000_000 + rank * (per_rank + 8)
+    song_i = 0
+    for name, fmt, seconds, count, chunk in groups:
+        n_in = seconds * RATE_IN
+        t = torch.arange(n_in, dtype=torch.float64, device=dev) / RATE_IN
+        g_rel, g_beat = 0.0, 0
+        first_chunk = True
+        for c0 in range(0, count, chunk):
+            S = min(chunk, count - c0)
+            f32 = torch.empty((S + 1, n_in), dtype=torch.float32, device=dev)
+            for i in range(S + 1):
+                synth_song(torch, f32[i], base_index + song_i + i, t)
+            song_i += S
+            if fmt == "f32":
+                stride = (n_in + 63) // 64 * 64 + 64
+                buf = torch.zeros(S * stride, dtype=torch.float32, device=dev)
+                buf.view(S, stride)[:, :n_in] = f32[:S]
+                host = f32[:S].cpu().numpy()
+                d_out = torch.zeros(S * 8, dtype=torch.int32, device=dev)
+                eng.analyze_device(E.FMT_F32, buf.data_ptr(), [i * stride for i in range(S)], [n_in] * S, d_out.data_ptr(),
+                                   stream=stream)
+            else:
+                n16 = 2 * (n_in // 2)
+                stride = (n16 + 63) // 64 * 64 + 64
+                buf = torch.zeros(S * stride, dtype=torch.int16, device=dev)
+                for i in range(S):
+                    buf[i * stride:i * stride + n16] = make_s16_stereo(torch, f32[i], f32[i + 1])
+                host = buf.view(S, stride)[:, :n16].cpu().numpy()
+                d_out = torch.zeros(S * 8, dtype=torch.int32, device=dev)
+                eng.analyze_device(E.FMT_S16, buf.data_ptr(), [i * stride for i in range(S)], [n16] * S, d_out.data_ptr(),
+                                   durations=[seconds] * S, stream=stream)
+            torch.cuda.synchronize()
+            got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=bliss_b200.RESULT_DTYPE)
+            del buf, f32
+            n_e = 16 if (first_chunk and seconds == 30) else (2 if first_chunk else 0)
+            r, Eref = cpu_leg_subprocess(host, 1, 0, energies=n_e)
+            kind = r["kind"]
+            cpu_s += r["seconds_per_step"]
+            ref = np.array(r["results"])
+            status_bad += int(np.count_nonzero(got["status"]))
+            for j, k in enumerate(comps):
+                rel = np.abs(got[k].astype(np.float64) - ref[:, j]) / np.maximum(np.abs(ref[:, j]), 1e-30)
+                max_rel[k] = max(max_rel[k], float(rel.max()))
+                g_rel = max(g_rel, float(rel.max()))
+            # tempo = 4 * beat / duration - 30.4 in float: equal tempo <=> equal onset count
+            ref_beat = np.rint((ref[:, 0] + 30.4) * seconds / 4.0).astype(np.int64)
+            bad = int(np.count_nonzero((got["beat"] != ref_beat) | (got["tempo"] != ref[:, 0].astype(np.float32))))
+            beat_mismatch += bad
+            g_beat += bad
+            for i in range(n_e):  # hop energies of a few songs: how often does the float accumulator land one ulp off?
+                Eg = eng.envelope_energy_f32(host[i]) if fmt == "f32" else eng.envelope_energy(host[i])
+                flips += int(np.count_nonzero(Eg != Eref[i]))
+                hops += int(Eg.size)
+                e_max_rel = max(e_max_rel, float(np.max(np.abs(Eg - Eref[i]) / np.maximum(Eref[i], 1e-300))))
+            n_done += S
+            first_chunk = False
+        per_group[name] = {"songs": count, "max_rel_err": g_rel, "beat_mismatches": g_beat}
+        del t
+    tot = torch.tensor([n_done, beat_mismatch, status_bad, flips, hops], dtype=torch.float64, device=dev)
+    mx = torch.tensor([max_rel[k] for k in comps] + [e_max_rel, cpu_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    tot, mx = tot.tolist(), mx.tolist()
+    worst = max(mx[:4])
+    return {"songs": int(tot[0]), "ranks": world, "checker": kind, "tolerance": 1e-4,
+            "beat_mismatches": int(tot[1]), "status_nonzero": int(tot[2]),
+            "max_rel_err": {k: mx[j] for j, k in enumerate(comps)},
+            "ok": bool(worst <= 1e-4 and tot[1] == 0 and tot[2] == 0),
+            "energy_hops_compared": int(tot[4]), "energy_flips": int(tot[3]),
+            "energy_flip_rate": (tot[3] / tot[4]) if tot[4] else None, "energy_max_rel_err": mx[4],
+            "groups_rank0": per_group, "cpu_seconds_max_rank": mx[5],
+            "mix": "per rank: 30-s and 3-min songs, half 44.1 kHz float32 (front-end path), half native int16 stereo with a "
+                   "decorrelated right channel; tempo compared exactly (<=> onset count), E[m] bit for bit on a sample"}
+
+
+# ------------------------------------------------------------------------------------------ configs[4]
+def chain_leg(torch, eng, E, dev, stream, rank, world, dist, barrier, max_over_ranks, buf, stride, n_in, B, per_gpu,
+              hbm_peak):
+    """BASELINE.json configs[4], chained: every rank analyses its share of world x per_gpu distinct synthetic songs in
+    batches of B (generated on the device, untimed, into the resident buffer), the force vectors are all-gathered
+    (NCCL, 16 B/song), and every rank computes its row slab of the all-pairs bl_distance matrix twice: fused nearest-
+    neighbour epilogue, and materialised in HBM (the write-bound form). Times are CUDA events, max over ranks."""
+    import bliss_b200
+    from bliss_b200 import parallel
+    n_batches = max(1, per_gpu // B)
+    per_gpu = n_batches * B
+    t = torch.arange(n_in, dtype=torch.float64, device=dev) / RATE_IN
+    d_res = torch.zeros(per_gpu * 8, dtype=torch.int32, device=dev)
+    offs, lens = [i * stride for i in range(B)], [n_in] * B
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    first = 2_000_000 + rank * per_gpu
+    analysis_ms, gen_s = 0.0, 0.0
+    for b in range(n_batches):
+        t0 = time.perf_counter()
+        for i in range(B):
+            synth_song(torch, buf[i * stride:i * stride + n_in], first + b * B + i, t)
+        torch.cuda.synchronize()
+        gen_s += time.perf_counter() - t0
+        ev0.record()
+        eng.analyze_device(E.FMT_F32, buf.data_ptr(), offs, lens, d_res.data_ptr() + b * B * 32, stream=stream)
+        ev1.record()
+        torch.cuda.synchronize()
+        analysis_ms += ev0.elapsed_time(ev1)
+    analysis_ms = max_over_ranks(analysis_ms)
+    rec = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=bliss_b200.RESULT_DTYPE)
+    bad = int(np.count_nonzero(rec["status"]))
+    local = d_res.view(torch.float32).view(per_gpu, 8)[:, :4].contiguous()
+    parallel.all_gather_vectors(local)  # NCCL channel set-up for this message size is not part of the measurement
+    barrier()
+    ev0.record()
+    allv, row0 = parallel.all_gather_vectors(local)
+    ev1.record()
+    barrier()
+    gather_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    n_total = allv.shape[0]
+    # the gathered table against an independent re-analysis: this rank re-generates the first songs of the NEXT rank's
+    # shard and analyses them itself (at world == 1: its own first songs, alone in a small batch)
+    K = min(64, B)
+    peer = (rank + 1) % world
+    for i in range(K):
+        synth_song(torch, buf[i * stride:i * stride + n_in], 2_000_000 + peer * per_gpu + i, t)
+    d_chk = torch.zeros(K * 8, dtype=torch.int32, device=dev)
+    eng.analyze_device(E.FMT_F32, buf.data_ptr(), offs[:K], lens[:K], d_chk.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    mine = d_chk.view(torch.float32).view(K, 8)[:, :4]
+    same = bool(torch.equal(mine.view(torch.int32), allv[peer * per_gpu:peer * per_gpu + K].view(torch.int32)))
+    # fused nearest-neighbour epilogue over this rank's rows
+    idx = torch.empty(per_gpu, dtype=torch.int32, device=dev)
+    dst = torch.empty(per_gpu, dtype=torch.float32, device=dev)
+    eng.distance_nearest_device(allv.data_ptr(), n_total, row0, per_gpu, idx.data_ptr(), dst.data_ptr(), 0, stream=stream)
+    barrier()
+    ev0.record()
+    eng.distance_nearest_device(allv.data_ptr(), n_total, row0, per_gpu, idx.data_ptr(), dst.data_ptr(), 0, stream=stream)
+    ev1.record()
+    barrier()
+    near_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    # materialised slab (per_gpu x n_total float32 in HBM)
+    slab = torch.empty((per_gpu, n_total), dtype=torch.float32, device=dev)
+    eng.distance_rows_device(allv.data_ptr(), n_total, row0, per_gpu, slab.data_ptr(), stream=stream)
+    barrier()
+    ev0.record()
+    eng.distance_rows_device(allv.data_ptr(), n_total, row0, per_gpu, slab.data_ptr(), stream=stream)
+    ev1.record()
+    barrier()
+    slab_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    slab_bytes = per_gpu * n_total * 4
+    # the fused epilogue against a brute-force scan of the materialised rows: same distance bit for bit, and no
+    # lower index at that distance (ties go to the lowest index, as a scan over bl_distance values would)
+    ok_near = True
+    rows_per = max(1, (1 << 28) // max(n_total, 1))
+    cols = torch.arange(n_total, device=dev, dtype=torch.int64)
+    for r0 in range(0, per_gpu, rows_per):
+        r1 = min(per_gpu, r0 + rows_per)
+        blk = slab[r0:r1].clone()
+        blk[torch.arange(r1 - r0, device=dev), torch.arange(row0 + r0, row0 + r1, device=dev)] = float("inf")
+        mn = blk.min(dim=1).values
+        first_idx = torch.where(blk == mn[:, None], cols[None, :], n_total).min(dim=1).values
+        ok_near = ok_near and bool(torch.equal(mn, dst[r0:r1])) and bool(torch.equal(first_idx, idx[r0:r1].long()))
+        del blk
+    flags = torch.tensor([1.0 if same else 0.0, 1.0 if ok_near else 0.0, float(-bad)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    flags = flags.tolist()
+    del slab, allv
+    songs_total = world * per_gpu
+    total_ms = analysis_ms + gather_ms + near_ms
+    return {"workload": f"BASELINE.json configs[4]: {songs_total} distinct synthetic 3-min songs end to end on {world} GPU(s) "
+                        f"({per_gpu} per GPU in batches of {B}) -> all-gather of the force vectors -> all-pairs bl_distance",
+            "songs": songs_total, "analysis_ms": analysis_ms, "analysis_songs_per_s": songs_total / (analysis_ms * 1e-3),
+            "all_gather_ms": gather_ms, "all_gather_bytes": songs_total * 16,
+            "nearest_ms": near_ms, "nearest_pairs_per_s": float(per_gpu) * n_total * world / (near_ms * 1e-3),
+            "chained_ms": total_ms, "chained_songs_per_s": songs_total / (total_ms * 1e-3),
+            "slab_ms": slab_ms, "slab_bytes_per_gpu": slab_bytes, "slab_gbs": slab_bytes / (slab_ms * 1e-3) / 1e9,
+            "slab_frac_hbm_write": slab_bytes / (slab_ms * 1e-3) / 1e9 / hbm_peak,
+            "gathered_vectors_bit_equal_reanalysis": bool(flags[0] == 1.0), "reanalysed_songs_per_rank": K,
+            "nearest_equals_bruteforce_over_slab": bool(flags[1] == 1.0), "status_nonzero": int(-flags[2]),
+            "generation_s_untimed": gen_s}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -313,6 +540,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    fp64_peak = max_over_ranks(eng.measure_fp64_peak())  # DFMA roofline denominator, measured here and now
+    barrier()
     eng.profile_reset()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -360,7 +589,7 @@ def run_ours(args):
         if name == "envelope_kernel":
             tf = FP64_FLOP_PER_HOP * hops * B / (per_launch_ms * 1e-3) / 1e12
             kernels[name]["fp64_tflops"] = tf
-            kernels[name]["frac_fp64"] = tf / DFMA_PEAK_TFLOPS
+            kernels[name]["frac_fp64"] = tf / fp64_peak
     dom = max(kernels, key=lambda k: kernels[k]["share"])
     traffic = None
     try:
@@ -369,9 +598,11 @@ def run_ours(args):
     except Exception:
         pass
     if dom == "envelope_kernel":
-        roofline = {"kernel": dom, "bound": "fp64", "achieved": kernels[dom]["fp64_tflops"], "peak": DFMA_PEAK_TFLOPS,
+        roofline = {"kernel": dom, "bound": "fp64", "achieved": kernels[dom]["fp64_tflops"], "peak": fp64_peak,
                     "unit": "TFLOP/s", "frac": kernels[dom]["frac_fp64"], "traffic": traffic,
-                    "peak_source": "measured DFMA throughput (tools/ubench.cu, profiles/r1_ubench.txt)",
+                    "peak_source": "DFMA throughput measured in this run before the timed steps (blx_measure_fp64_peak); "
+                                   f"round-1 microbenchmark: {DFMA_PEAK_TFLOPS} (profiles/r1_ubench.txt)",
+                    "alg_flop_per_launch": FP64_FLOP_PER_HOP * hops * B,
                     "note": "FP64-pipe bound (SURVEY.md §0 F5, §7.3 H3); its HBM fraction is in roofline_kernels"}
     else:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak,
@@ -483,14 +714,24 @@ def run_ours(args):
         ev1.record()
         barrier()
         near_ms = max_over_ranks(ev0.elapsed_time(ev1))
-        # spot check: the reported neighbour really is at the reported distance
-        probe = slice(0, min(hi - lo, 4096))
-        chk = torch.linalg.vector_norm(local[probe] - allv[idx[probe].long()], dim=1)
-        ok = bool(torch.allclose(chk, dst[probe], rtol=1e-5, atol=1e-6))
+        # check on a row sample against a brute-force scan in plain float32 torch ops (separate sub / mul / add kernels:
+        # the roundings of bl_distance, no FMA): the nearest song's distance bit for bit and the lowest index at it
+        ok = True
+        probe = torch.arange(0, hi - lo, max(1, (hi - lo) // 64), device=dev)[:64]
+        cols = torch.arange(nv, device=dev, dtype=torch.int64)
+        for r in probe.tolist():
+            dlt = local[r][None, :] - allv
+            sq = dlt * dlt
+            dd = torch.sqrt(((sq[:, 0] + sq[:, 1]) + sq[:, 2]) + sq[:, 3])
+            dd[row0 + r] = float("inf")
+            mn = dd.min()
+            first_idx = int(torch.where(dd == mn, cols, nv).min())
+            ok = ok and float(mn) == float(dst[r]) and first_idx == int(idx[r])
         all_pairs = {"workload": f"BASELINE.json configs[3]: all-pairs bl_distance over {nv} force vectors, fused nearest-"
                                  "neighbour epilogue (matrix never materialised), rows sharded by rank",
                      "n_vectors": nv, "pairs_per_s": float(nv) * nv / (near_ms * 1e-3), "ms": near_ms,
-                     "all_gather_ms": gather_ms, "all_gather_bytes": nv * 16, "spot_check_ok": ok}
+                     "all_gather_ms": gather_ms, "all_gather_bytes": nv * 16, "bruteforce_rows_checked": int(probe.numel()),
+                     "bruteforce_argmin_ok": ok}
         del table, allv
 
     # ---------------- e2e: host buffers through the C-ABI, copies inside the timed region
@@ -544,7 +785,7 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         S = max(2, min(4 * cores, 128, B))  # ~10-20 s of CPU work on the box's cores
         f32 = np.stack([buf[i * stride:i * stride + n_in].cpu().numpy() for i in range(S)])
-        r = cpu_leg_subprocess(f32, 1, 0)
+        r, _ = cpu_leg_subprocess(f32, 1, 0)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["workers"], "kind": r["kind"],
                         "sample": f"first {S} songs of the step's batch, {r['seconds_per_step']:.2f} s wall on {r['workers']} "
                                   f"worker processes ({cores} host cores); front-end excluded; reference src/*.c compiled "
@@ -554,6 +795,19 @@ def run_ours(args):
         rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)
         parity = {"songs": S, "max_rel_err": float(rel.max()), "tolerance": 1e-4, "ok": bool(rel.max() <= 1e-4)}
 
+    # ---------------- parity campaign (all ranks) and configs[4] chained
+    campaign = None
+    if args.parity_songs > 0 and not args.no_cpu:
+        t0 = time.perf_counter()
+        campaign = parity_campaign(torch, eng, E, dev, stream, rank, world, args.parity_songs, dist)
+        campaign["wall_s"] = time.perf_counter() - t0
+        if not campaign["ok"]:
+            log(f"[rank {rank}] PARITY CAMPAIGN FAILED: {campaign}")
+    chain = None
+    if args.chain_songs > 0:
+        chain = chain_leg(torch, eng, E, dev, stream, rank, world, dist, barrier, max_over_ranks, buf, stride, n_in, B,
+                          args.chain_songs, hbm_peak)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -561,7 +815,7 @@ def run_ours(args):
             "dtype": "f64 (envelope) + f32 (spectrum) + int64 (statistics)", "data": "synthetic",
             "config": workload_config(args, B, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_kernels": kernels, "spectral_only": spectral, "native_s16": native, "all_pairs": all_pairs, "cpu_baseline": cpu_baseline,
-            "parity": parity,
+            "parity": campaign if campaign is not None else parity, "parity_sample": parity, "configs4_chained": chain,
         }
         print(json.dumps(line), flush=True)
     eng.close()
@@ -584,10 +838,16 @@ def main():
     ap.add_argument("--no-spectral", action="store_true")
     ap.add_argument("--no-distance", action="store_true")
     ap.add_argument("--distance-vectors", type=int, default=1 << 20)
+    ap.add_argument("--parity-songs", type=int, default=4096, help="songs of the parity campaign, all ranks together (0 = off)")
+    ap.add_argument("--chain-songs", type=int, default=32768,
+                    help="songs per GPU of the configs[4] leg (analysis -> all-gather -> all-pairs); 0 = off")
     ap.add_argument("--_cpu-leg", dest="cpu_leg_path", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--_cpu-energies", dest="cpu_energies", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--_cpu-energy-path", dest="cpu_energy_path", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_leg_path:
-        r = cpu_leg(np.load(args.cpu_leg_path, mmap_mode="r"), args.steps, args.warmup)
+        r = cpu_leg(np.load(args.cpu_leg_path, mmap_mode="r"), args.steps, args.warmup, energies=args.cpu_energies,
+                    energy_path=args.cpu_energy_path)
         print(json.dumps(r), flush=True)
         return 0
     if args.impl == "reference":

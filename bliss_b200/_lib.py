@@ -59,8 +59,9 @@ BLX_H_SYMBOLS = [
     "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_device", "blx_spectral_device",
     "blx_distance_matrix", "blx_cosine_matrix", "blx_distance_rows_device", "blx_distance_nearest_device",
     "blx_mean_variance_s16", "blx_rectangular_filter", "blx_frontend_f32", "blx_envelope_energy_s16",
-    "blx_frequency_spectrum_s16", "blx_histogram_s16", "blx_envelope_tail",
+    "blx_frequency_spectrum_s16", "blx_histogram_s16", "blx_envelope_tail", "blx_envelope_energy_f32",
     "blx_profile_enable", "blx_profile_reset", "blx_profile_read", "blx_kernel_name", "blx_launch_count",
+    "blx_measure_fp64_peak",
 ]
 
 _lib = None
@@ -114,6 +115,8 @@ def load():
     L.blx_frontend_f32.argtypes = [vp, c_f32p, ctypes.c_int64, c_i16p]
     L.blx_envelope_energy_s16.restype = ctypes.c_int
     L.blx_envelope_energy_s16.argtypes = [vp, c_i16p, ctypes.c_int, c_f64p]
+    L.blx_envelope_energy_f32.restype = ctypes.c_int
+    L.blx_envelope_energy_f32.argtypes = [vp, c_f32p, ctypes.c_int64, c_f64p]
     L.blx_frequency_spectrum_s16.restype = ctypes.c_int
     L.blx_frequency_spectrum_s16.argtypes = [vp, c_i16p, ctypes.c_int, ctypes.c_int, c_f32p]
     L.blx_histogram_s16.restype = ctypes.c_int
@@ -126,6 +129,8 @@ def load():
     L.blx_profile_reset.argtypes = [vp]
     L.blx_profile_read.restype = ctypes.c_int
     L.blx_profile_read.argtypes = [vp, c_f32p, c_i32p]
+    L.blx_measure_fp64_peak.restype = ctypes.c_int
+    L.blx_measure_fp64_peak.argtypes = [vp, c_f64p, c_f64p]
     L.blx_kernel_name.restype = ctypes.c_char_p
     L.blx_kernel_name.argtypes = [ctypes.c_int]
     L.blx_launch_count.restype = ctypes.c_longlong

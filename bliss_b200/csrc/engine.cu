@@ -741,6 +741,53 @@ extern "C" int blx_envelope_energy_s16(blx_engine *e, const int16_t *pcm, int n_
     return BLX_OK;
 }
 
+extern "C" int blx_envelope_energy_f32(blx_engine *e, const float *pcm, int64_t n_in, double *energy) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!pcm || n_in < 2 || !energy) return fail(BLX_ERR_ARG, "bad arguments");
+    const float *ptrs[1] = {pcm};
+    const int64_t ns[1] = {n_in};
+    blx_result r;
+    e->next_slot = 0;
+    rc = blx_analyze_batch_f32(e, ptrs, ns, 1, BLX_DO_ALL, &r);
+    if (rc) return rc;
+    const int nb = 2 * (int)((2 * (n_in / 2)) / kWin);
+    if (nb > 0) CK(cudaMemcpy(energy, e->slot[0].energy.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost));
+    return BLX_OK;
+}
+
+// ---------------------------------------------------------------- roofline denominators
+extern "C" int blx_measure_fp64_peak(blx_engine *e, double *tflops, double *sm_mhz_nominal) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!tflops) return fail(BLX_ERR_ARG, "null output");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, e->device));
+    const int threads = 1024, blocks = prop.multiProcessorCount * 2, iters = 1 << 15;
+    CK(e->scratch_a.reserve((size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) { // the first repetitions warm the clocks up
+        CK(cudaEventRecord(a, e->compute));
+        CK(launch_dfma_peak(static_cast<double *>(e->scratch_a.p), blocks, threads, iters, e->compute));
+        CK(cudaEventRecord(b, e->compute));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep >= 2 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device);
+    if (sm_mhz_nominal) *sm_mhz_nominal = khz / 1000.0;
+    return BLX_OK;
+}
+
 // ---------------------------------------------------------------- stage-level views (kernel parity tests)
 extern "C" int blx_frequency_spectrum_s16(blx_engine *e, const int16_t *pcm, int n_samples, int channels, float *ps) {
     int rc = check_engine(e);

@@ -65,6 +65,7 @@ int distance_nearest_splits(int n, int n_rows, bool with_sum);
 cudaError_t launch_distance_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_dist,
                                     double *d_sum, unsigned long long *d_packed, int splits, cudaStream_t st);
 cudaError_t launch_rect_filter(double *d_out, const double *d_in, int n, int width, cudaStream_t st);
+cudaError_t launch_dfma_peak(double *d_scratch, int blocks, int threads, int iters, cudaStream_t st);
 cudaError_t launch_frontend(const float *d_in, long long n_in, short *d_out, cudaStream_t st);
 
 } // namespace blx

@@ -163,6 +163,14 @@ class Engine:
         self._ck(self._lib.blx_envelope_energy_s16(self._h, a.ctypes.data_as(L.c_i16p), len(a), E.ctypes.data_as(L.c_f64p)))
         return E[:nb]
 
+    def envelope_energy_f32(self, x):
+        """Hop energies of a 44.1 kHz mono float32 song through the fused path (front-end + doubled-mono envelope)."""
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        nb = 2 * ((2 * (len(a) // 2)) // 512)
+        E = np.zeros(max(nb, 1), dtype=np.float64)
+        self._ck(self._lib.blx_envelope_energy_f32(self._h, a.ctypes.data_as(L.c_f32p), len(a), E.ctypes.data_as(L.c_f64p)))
+        return E[:nb]
+
     def frequency_spectrum(self, pcm, channels=2):
         """Per-bin power (sum over frames of |X_d|^2, d = 1..255) before the scalar epilogue; 257 floats."""
         a = np.ascontiguousarray(pcm, dtype=np.int16)
@@ -205,6 +213,12 @@ class Engine:
         n = (ctypes.c_int * K_COUNT)()
         self._ck(self._lib.blx_profile_read(self._h, ms, n))
         return {self._lib.blx_kernel_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(K_COUNT)}
+
+    def measure_fp64_peak(self):
+        """Measured DFMA throughput of this device right now, TFLOP/s (the envelope kernel's roofline denominator)."""
+        tf, mhz = ctypes.c_double(0), ctypes.c_double(0)
+        self._ck(self._lib.blx_measure_fp64_peak(self._h, ctypes.byref(tf), ctypes.byref(mhz)))
+        return tf.value
 
     def launch_count(self):
         return int(self._lib.blx_launch_count(self._h))

@@ -147,6 +147,9 @@ int blx_frontend_f32(blx_engine *e, const float *pcm, int64_t n_in, int16_t *out
 /* Envelope intermediates for kernel-level parity tests: hop energies E[m]
  * (reference src/tempo_atk_sort.c:150), 2 * (n_samples / 512) doubles, host. */
 int blx_envelope_energy_s16(blx_engine *e, const int16_t *pcm, int n_samples, double *energy);
+/* Same through the float32 path (front-end in pass 1, doubled-mono form of the envelope kernel):
+ * 2 * ((2 * (n_in / 2)) / 512) doubles. */
+int blx_envelope_energy_f32(blx_engine *e, const float *pcm, int64_t n_in, double *energy);
 
 /* Per-bin power spectrum of the frequency analyser BEFORE its scalar epilogue: ps[d] = sum over frames
  * of |X_d|^2, d = 1..255 (reference src/frequency_sort.c:88-93); ps[0] = ps[256] = 0. 257 floats, host. */
@@ -178,6 +181,11 @@ int blx_profile_enable(blx_engine *e, int on);
 int blx_profile_reset(blx_engine *e);
 int blx_profile_read(blx_engine *e, float *ms /* [BLX_K_COUNT] */, int *launches /* [BLX_K_COUNT] */);
 const char *blx_kernel_name(int kernel_id);
+
+/* The FP64 roofline denominator, measured on this device now: best of several launches of a kernel that
+ * only issues independent DFMA chains (2 flop each) from 2 x 1024 threads per SM. MEASURED_PEAKS.json has
+ * no FP64 entry, and the envelope kernel is bound by the FP64 pipe. */
+int blx_measure_fp64_peak(blx_engine *e, double *tflops, double *sm_mhz_nominal /* may be NULL */);
 
 /* Total kernels launched by this engine since creation (bench.py's gpu_launches). */
 long long blx_launch_count(blx_engine *e);
