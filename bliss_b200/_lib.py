@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbliss.so")
+# BLISS_B200_LIB: another build of the same library (kernel A/B experiments, tools/ab_envelope.sh)
+LIB_PATH = os.environ.get("BLISS_B200_LIB") or os.path.join(_HERE, "libbliss.so")
 
 c_i16p = ctypes.POINTER(ctypes.c_int16)
 c_f32p = ctypes.POINTER(ctypes.c_float)

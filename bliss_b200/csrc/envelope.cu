@@ -1,4 +1,4 @@
-// envelope.cu — hop energies of the envelope analyser in FP64 (kernel id BLX_K_ENVELOPE).
+// envelope.cu — hop energies of the envelope analyser (kernel id BLX_K_ENVELOPE).
 //
 // Replaces the hot loop of reference src/tempo_atk_sort.c:109-153: normalise the whole
 // interleaved int16 stream to zero mean / unit variance, and for every hop of 256 samples
@@ -18,94 +18,169 @@
 // sum. The raw int16 samples of the next pair are fetched by the warp's own 1-D bulk copy
 // (cp.async.bulk / UBLKCP, one mbarrier per buffer) while the FFTs of the current pair run. There
 // is no block-wide barrier after set-up, so the warps of an SM drift apart and the FP64-bound
-// phases (FIR, FFT) of some overlap the latency-bound phase (accumulation chain) of others.
+// phases (FFT) of some overlap the latency-bound phase (accumulation chain) of others.
+//
+// The FIR sums are EXACT: the reference's taps are decimal literals of seven digits, so c_k = C_k * 1e-7
+// with integer C_k (|C_k| < 2^24), the samples are int16, and x = (s / 32768 - mean_d) / var_d (reference
+// src/tempo_atk_sort.c:110-113) is affine in the raw sample s:
+//   y = A * 1e-7 * (sum C_k s_k) - Bm * (sum c_k),  A = 1 / (32768 var_d), Bm = mean_d / var_d.
+// sum C_k s_k < 2^44 is an integer whether it is accumulated in FP64 (the default: one DFMA per tap, no
+// rounding below 2^53) or in 64-bit integers (BLX_ENV_FIR_INT), and it is normalised with one FMA per
+// output. The result is the exact filter output rounded once; the reference rounds after every product and
+// sum, so the two differ by ~1e-16 relative, like any two summation orders - nine orders of magnitude below
+// the 1e-7 onset-count cliff.
 //
 // DUP = true: the stream is a mono signal u with every sample doubled (L = R), stored once
 // (x[2 i] = x[2 i + 1] = u[i], the decimated stream pass 1 writes for float32 input). The 17 taps
 // then fold into two 9-tap filters over u, one for even and one for odd outputs.
 //
 // The float accumulation s <- (float)((double)s + p_k), k = 0..256, is a chain of 257 dependent
-// roundings (~50-75 cycles each on the FP64 + conversion pipes): run naively it idles the SM. It is
-// evaluated by the 16 lanes that hold the hop's spectrum:
+// roundings (~50 cycles each on the FP64 + conversion pipes): run naively it idles the SM. It is
+// evaluated by the 16 lanes that hold the hop's spectrum (float_chain below):
 //   while s stays inside one binade [2^e, 2^(e+1)) its float grid is g = 2^(e-23) and
 //   RN_g(s + p) = s + RN_g(p) because s is a multiple of g; so with q = s / g (a 24-bit integer)
 //   the chain is q += I_k with I_k = RN_g(p_k) / g, which one double addition p_k + 1.5 * 2^52 * g
 //   leaves in the low mantissa word.
-// float_chain (below) predicts the binade of every bin from an exact double prefix scan of the
-// spectrum, converts every bin once at its predicted grid, takes the few binade crossings in order
-// through the reference's own double-add / float-convert step, and verifies every prediction on
-// the way; the rare hop that fails is redone by float_chain_rounds / chain_round, the first form of
-// the algorithm: one prefix-scan round per binade (every lane converts its 16 bins at the current
-// grid, the first bin k* at which q + prefix reaches 2^24 is found with a ballot, bin k* is added
-// with the reference step, the scan restarts after k*).
+// Which binade the sum is in when a bin is added is PREDICTED from the exact double prefix sum of the
+// spectrum, in groups of four bins: a group whose prefix keeps its exponent is added as integers, the
+// few others (~3 per hop) bin by bin with the reference's own step; every prediction is verified on
+// the way and the rare hop that fails is redone by float_chain_rounds / chain_round, the first form
+// of the algorithm (one prefix-scan round per binade).
 // The result equals the reference's chain except when s + p_k lies within 2^-29 grid units of a
 // rounding midpoint (the reference rounds to double, then to float; exact ties follow the parity of
 // the magic constant instead of q).
-//
-// FP64 throughout. FMA contraction and the folded / corrected summation orders differ from the
-// reference's (which has no FMA) by ~1e-16 relative in E[m], nine orders of magnitude below the
-// 1e-7 onset-count cliff measured in SURVEY.md App. B.
 #include "blx_common.cuh"
 #include "fft16.cuh"
 #include "kernels.h"
 
 namespace blx {
 
+// Build-time switches for A/B measurements (tools/ab_envelope.sh); the defaults are the measured best.
+#ifndef BLX_ENV_WARPS
+#define BLX_ENV_WARPS 8 // warps per CTA, doubled-mono form
+#endif
+#ifndef BLX_ENV_WARPS_S16
+#define BLX_ENV_WARPS_S16 8 // warps per CTA, interleaved stereo form (larger raw buffers: 8 is what two CTAs per SM hold)
+#endif
+#ifndef BLX_ENV_FIR_INT
+// 0: the FIR sums in FP64 over the integer taps (DFMA, exact: every partial sum is an integer below 2^53);
+// 1: in 64-bit integers (IMAD.WIDE). Measured on B200 (tools/ab_envelope.sh, 1 024 songs): 38.9 ms against 42.2 ms -
+// ptxas splits every mad.wide into a multiply and a 3-input 64-bit add, two issue slots per tap, and the kernel
+// is bound by dependent-issue latency, not by the FP64 pipe (40 % busy).
+#define BLX_ENV_FIR_INT 0
+#endif
+
 namespace {
-constexpr int kEnvThreads = 256;                 // 8 independent warps
-constexpr int kEnvWarps = kEnvThreads / 32;
 constexpr int kPairsPerWarp = 32;                // a warp owns 64 consecutive hops
-constexpr int kHopsPerCta = 2 * kPairsPerWarp * kEnvWarps;
 constexpr int kSlotBytes = kHop * 8;             // one block of 256 FIR outputs (128 cells of 16 bytes)
 
-// Shared-memory plan. Per warp: the FFT exchange buffers of its two hops (whose first 4 KB first hold
-// the two new FIR blocks of the pair), the carry block, two raw-sample buffers and their mbarriers.
+// Shared-memory plan. Per warp: the FFT exchange buffers of its two hops (the first 2 KB first hold
+// the FIR block B + 1 of the pair), the carry block, two raw-sample buffers and their mbarriers.
 // A raw buffer holds r[i] = stream element blk * (B + 1) - pre + i, B = first block (= hop) of the pair:
 // `pre` samples in front, then the two new blocks.
 template <bool DUP> struct EG {
+    static constexpr int warps = DUP ? BLX_ENV_WARPS : BLX_ENV_WARPS_S16; // independent warps per CTA
+    static constexpr int threads = 32 * warps;
+    static constexpr int hops_per_cta = 2 * kPairsPerWarp * warps;
     static constexpr int pre = DUP ? 8 : 16;     // raw elements in front of a block that its FIR reads
     static constexpr int blk = DUP ? 128 : 256;  // raw elements per block
     static constexpr int blk_bytes = blk * 2;
     static constexpr int per_thread = blk / 16;  // raw elements whose outputs one lane computes
     static constexpr int taps = DUP ? 8 : 16;    // head-correction terms per lane
-    static constexpr int row = taps + 2;         // doubles per head-table row: taps, D, pad
     static constexpr int raw_bytes = ((pre + 2 * blk) * 2 + 63) / 64 * 64;
-    static constexpr int w_xchg = 0;                                  // double2[2][272]; FIR blocks B+1, B+2 at +0, +2048
-    static constexpr int w_carry = w_xchg + 2 * kXchgElems * 16;      // FIR block B
+    static constexpr int w_xchg = 0;                                  // double2[2][272]; FIR block B + 1 at +0
+    static constexpr int w_carry = w_xchg + 2 * kXchgElems * 16;      // FIR block B, then B + 2
     static constexpr int w_raw = w_carry + kSlotBytes;                // 2 raw buffers
     static constexpr int w_bar = w_raw + 2 * raw_bytes;               // 2 mbarriers
     static constexpr int w_bytes = (w_bar + 16 + 127) / 128 * 128;
-    static constexpr int off_tab = kEnvWarps * w_bytes;               // double[16][row] head table
-    static constexpr int bytes = off_tab + 16 * row * 8;
+    static constexpr int off_tabi = warps * w_bytes;              // int[16][taps] head table (integer taps)
+    static constexpr int off_tabd = off_tabi + 16 * taps * 4;         // double[16]: sum of the dropped taps
+    static constexpr int bytes = off_tabd + 16 * 8;
     static_assert(bytes <= 115712, "two CTAs per SM");
 };
 
-// reference include/bandpass_coeffs.h:1-7 — coeffs[0][0..8]; the filter is symmetric.
-__device__ __forceinline__ double fir_tap(int k) {
-    constexpr double c[9] = {-0.0023470, 0.0044613, -0.0114627, 0.0226382, -0.0405147,
-                             0.0580037,  -0.0779167, 0.0882711, 0.9065095};
+// reference include/bandpass_coeffs.h:1-7 — coeffs[0][0..8]; the filter is symmetric. The literals have seven
+// decimals: kTapI[k] = coeffs[0][k] * 1e7 exactly.
+__device__ __forceinline__ constexpr int tap_i(int k) {
+    constexpr int c[9] = {-23470, 44613, -114627, 226382, -405147, 580037, -779167, 882711, 9065095};
     return c[k];
 }
-// Coefficient that multiplies x[j - m] in the 17-tap FIR, m = 0..16 (symmetric; reference
-// include/bandpass_coeffs.h:1-7 and the loop of reference src/tempo_atk_sort.c:124-137).
-__device__ __forceinline__ double fir_coef_of_lag(int m) { return fir_tap(m <= 8 ? m : 16 - m); }
-// Folded taps of the doubled mono stream: even output 2 n = sum_m fold_e(m) u[n - m], odd output
-// 2 n + 1 = sum_m fold_d(m) u[n - m], m = 0..8.
-__device__ __forceinline__ double fold_e(int m) { return m == 0 ? fir_coef_of_lag(0) : fir_coef_of_lag(2 * m - 1) + fir_coef_of_lag(2 * m); }
-__device__ __forceinline__ double fold_d(int m) { return fir_coef_of_lag(2 * m) + (m < 8 ? fir_coef_of_lag(2 * m + 1) : 0.0); }
-// the same three functions with a run-time argument (table set-up only)
 __constant__ double c_fir_half[9] = {-0.0023470, 0.0044613, -0.0114627, 0.0226382, -0.0405147,
                                      0.0580037,  -0.0779167, 0.0882711, 0.9065095};
-__device__ __forceinline__ double fir_coef_rt(int m) { return c_fir_half[m <= 8 ? m : 16 - m]; }
-__device__ __forceinline__ double fold_e_rt(int m) { return m == 0 ? fir_coef_rt(0) : fir_coef_rt(2 * m - 1) + fir_coef_rt(2 * m); }
-__device__ __forceinline__ double fold_d_rt(int m) { return fir_coef_rt(2 * m) + (m < 8 ? fir_coef_rt(2 * m + 1) : 0.0); }
+__constant__ int c_fir_half_i[9] = {-23470, 44613, -114627, 226382, -405147, 580037, -779167, 882711, 9065095};
+// Integer coefficient that multiplies x[j - m] in the 17-tap FIR, m = 0..16 (symmetric; reference
+// include/bandpass_coeffs.h:1-7 and the loop of reference src/tempo_atk_sort.c:124-137).
+__device__ __forceinline__ constexpr int lag_i(int m) { return tap_i(m <= 8 ? m : 16 - m); }
+// Folded taps of the doubled mono stream: even output 2 n = sum_m fold_e(m) u[n - m], odd output
+// 2 n + 1 = sum_m fold_d(m) u[n - m], m = 0..8.
+__device__ __forceinline__ constexpr int fold_e_i(int m) { return m == 0 ? lag_i(0) : lag_i(2 * m - 1) + lag_i(2 * m); }
+__device__ __forceinline__ constexpr int fold_d_i(int m) { return lag_i(2 * m) + (m < 8 ? lag_i(2 * m + 1) : 0); }
+// the same with a run-time argument (table set-up only), integer and double
+__device__ __forceinline__ int lag_i_rt(int m) { return c_fir_half_i[m <= 8 ? m : 16 - m]; }
+__device__ __forceinline__ int fold_e_i_rt(int m) { return m == 0 ? lag_i_rt(0) : lag_i_rt(2 * m - 1) + lag_i_rt(2 * m); }
+__device__ __forceinline__ int fold_d_i_rt(int m) { return lag_i_rt(2 * m) + (m < 8 ? lag_i_rt(2 * m + 1) : 0); }
+__device__ __forceinline__ double lag_d_rt(int m) { return c_fir_half[m <= 8 ? m : 16 - m]; }
+__device__ __forceinline__ double fold_e_d_rt(int m) { return m == 0 ? lag_d_rt(0) : lag_d_rt(2 * m - 1) + lag_d_rt(2 * m); }
+__device__ __forceinline__ double fold_d_d_rt(int m) { return lag_d_rt(2 * m) + (m < 8 ? lag_d_rt(2 * m + 1) : 0.0); }
 
-// Where bin k (0..256) of a hop's power spectrum lives in its exchange buffer: lane b reads its bins
-// 16 b + 1 .. 16 b + 16 at stride 17 doubles (conflict free); bins 0..16 are at their own index.
-__device__ __forceinline__ int pbin(int k) { return k + ((k + 15) >> 4) - 1 + (k == 0); }
+// acc + x * C / acc + x * c as ONE 32 x 32 + 64-bit multiply-add (IMAD.WIDE); the C++ form (long long)c * x widens first
+// and costs a 64-bit multiply sequence
+template <int C> __device__ __forceinline__ long long madw(int x, long long acc) {
+    asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "n"(C));
+    return acc;
+}
+__device__ __forceinline__ long long madw_r(int x, int c, long long acc) {
+    asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "r"(c));
+    return acc;
+}
+// the nine folded taps of output pair `o` of a lane (doubled mono stream), m = M..8
+template <int M> __device__ __forceinline__ void fir_dup_taps(const int (&u)[16], int o, long long &ye, long long &yd) {
+    ye = madw<fold_e_i(M)>(u[8 + o - M], ye);
+    yd = madw<fold_d_i(M)>(u[8 + o - M], yd);
+    if constexpr (M < 8) fir_dup_taps<M + 1>(u, o, ye, yd);
+}
+// the symmetric tap pairs k = K..7 of output `o` of a lane (interleaved stereo stream)
+template <int K> __device__ __forceinline__ void fir_sym_taps(const int (&xv)[32], int o, long long &y) {
+    y = madw<tap_i(K)>(xv[o + 16 - K] + xv[o + K], y);
+    if constexpr (K < 7) fir_sym_taps<K + 1>(xv, o, y);
+}
+
+// (double)v for |v| < 2^51: one integer add on the high word (the constant's low word is 0) and one DADD.
+__device__ __forceinline__ double i64_to_double(long long v) {
+    return __longlong_as_double(v + 0x4338000000000000ll) - 6755399441055744.0;
+}
+
+// ---------------------------------------------------------------- power spectrum layout
+// Where bin k (0..256) of a hop's power spectrum lives in its exchange buffer (doubles). Lane b of the
+// accumulation owns bins 16 b + 1 .. 16 b + 16 = row b, 18 doubles apart (16-byte aligned rows, conflict-free
+// 128-bit reads): element i < 15 at slot i, element 15 at slot 17 in rows 0..6 and at slot 15 in rows 7..15
+// (whichever keeps the 16 lanes that write one bin each - bins l + 16 d, or 256 - l - 16 d - on 16 different
+// banks); bin 0 at slot 15 of row 0.
+constexpr int kPRow = 18;
+__host__ __device__ constexpr int pslot15(int b) { return b <= 6 ? 17 : 15; }
+__device__ __forceinline__ int pidx(int k) {
+    if (k == 0) return 15;
+    const int b = (k - 1) >> 4, i = (k - 1) & 15;
+    return kPRow * b + (i == 15 ? pslot15(b) : i);
+}
+static_assert(kPRow * 16 * 8 <= kXchgElems * 16, "spectrum fits the exchange buffer");
+
+// This lane's 16 bins (row lane16) from shared memory: nine 128-bit loads.
+__device__ __forceinline__ void load_row(const double *xr, int lane16, double (&pv)[16]) {
+    const double2 *row = reinterpret_cast<const double2 *>(xr + kPRow * lane16);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const double2 t = row[i];
+        pv[2 * i] = t.x;
+        pv[2 * i + 1] = t.y;
+    }
+    const double2 a = row[7], b = row[8];
+    pv[14] = a.x;
+    pv[15] = (lane16 <= 6) ? b.y : a.y;
+}
 
 // sum_fft of reference src/tempo_atk_sort.c:142-150 for the two hops of a warp, one per half-warp (see
-// the header comment). xr[pbin(k)] = |X_k|^2 of this lane's half-warp; `active` is false for a
+// the header comment). xr[pidx(k)] = |X_k|^2 of this lane's half-warp; `active` is false for a
 // half-warp without a hop (last tile of a song). Returns (double)sum_fft on every lane of the half.
 // All 32 lanes run the same control flow, so every shuffle / vote uses the full mask (a partial-mask
 // shuffle compiles to a divergence-safe sequence several times slower); the state of a chain is
@@ -124,7 +199,7 @@ __device__ __forceinline__ void chain_round(const double *xr, const double (&pv)
     const bool normal = (ex >= 1023 - 126) && (ex <= 1023 + 127);
     if (!done && !normal) {
         // zero, subnormal, inf or nan: no binade to scan in; one plain reference step
-        r = (double)(float)(r + xr[pbin(kdone + 1)]);
+        r = (double)(float)(r + xr[pidx(kdone + 1)]);
         kdone += 1;
         if (kdone == 256) done = true;
     }
@@ -150,7 +225,7 @@ __device__ __forceinline__ void chain_round(const double *xr, const double (&pv)
     const int cur = (kdone - 1) >> 4; // lane that holds bin kdone; its bins up to kdone are consumed
     {
         const int kk = 16 * cur + 1 + lane16; // the half-warp measures the consumed part of lane `cur`
-        const int c = (kk <= kdone) ? increment(xr[pbin(kk)]) : 0;
+        const int c = (kk <= kdone) ? increment(xr[pidx(kk)]) : 0;
         const int c_lo = __reduce_add_sync(full, (threadIdx.x & 16) ? 0 : c);
         const int c_hi = __reduce_add_sync(full, (threadIdx.x & 16) ? c : 0);
         const int consumed = (threadIdx.x & 16) ? c_hi : c_lo;
@@ -176,7 +251,7 @@ __device__ __forceinline__ void chain_round(const double *xr, const double (&pv)
     }
     // (3) the bin inside lane src
     const int kk = 16 * src + 1 + lane16;
-    const int inc1 = (scan && lanes_over && kk > kdone) ? increment(xr[pbin(kk)]) : 0;
+    const int inc1 = (scan && lanes_over && kk > kdone) ? increment(xr[pidx(kk)]) : 0;
     int incl1 = inc1;
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) {
@@ -191,7 +266,7 @@ __device__ __forceinline__ void chain_round(const double *xr, const double (&pv)
         if (lanes_over) {
             const int kstar = 16 * src + 1 + bsrc;
             const double sq = __hiloint2double((ex << 20) | ((qb & 0x7FFFFF) >> 3), (qb & 7) << 29);
-            r = (double)(float)(sq + xr[pbin(kstar)]); // reference src/tempo_atk_sort.c:147
+            r = (double)(float)(sq + xr[pidx(kstar)]); // reference src/tempo_atk_sort.c:147
             kdone = kstar;
             if (kdone == 256) done = true;
         } else {
@@ -207,8 +282,7 @@ __device__ __noinline__ double float_chain_rounds(const double *xr, int lane16, 
     const unsigned full = 0xffffffffu;
     const int lane_base = (threadIdx.x & 16);
     double pv[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pv[i] = xr[17 * lane16 + 1 + i]; // bins 16 lane16 + 1 + i
+    load_row(xr, lane16, pv); // bins 16 lane16 + 1 + i
     double r = r16;
     int kdone = 16; // bins 0..kdone are in r
     bool done = !active;
@@ -216,50 +290,57 @@ __device__ __noinline__ double float_chain_rounds(const double *xr, int lane16, 
     return r;
 }
 
-// Byte offsets of the per-hop scratch behind the 272 doubles of the power spectrum (the hop's FFT exchange
-// buffer is 4352 bytes): integer prefix in front of every bin of lanes' bins j = 16 b + i (vector v of lane b at
-// 16 (16 v + b)), its total, the predicted exponent at the end, the predicted exponent (top 16 bits of the
-// running double sum) in front of every bin, and each lane's mask of binade-crossing bins.
-constexpr int kAuxPb = 0, kAuxTot = 1024, kAuxEnd = 1028, kAuxEg = 1040, kAuxMask = 1552;
-static_assert(272 * 8 + kAuxMask + 32 <= kXchgElems * 16, "scratch fits behind the spectrum");
+// the float q (an integer 2^23 <= q < 2^24 on the grid of binade `ex`) as a double
+__device__ __forceinline__ double grid_to_double(int ex, unsigned q) {
+    return __hiloint2double((ex << 20) | (int)((q & 0x7FFFFFu) >> 3), (int)((q & 7u) << 29));
+}
 
 // sum_fft of reference src/tempo_atk_sort.c:142-150 for the two hops of a warp, one per half-warp:
-// s <- (float)((double)s + p_k), k = 0..256, with p_k = xr[pbin(k)]. `active` is false for a half-warp
+// s <- (float)((double)s + p_k), k = 0..256, with p_k = xr[pidx(k)]. `active` is false for a half-warp
 // without a hop. Returns (double)sum_fft on every lane of the half-warp.
 //
 // While s stays inside one binade [2^e, 2^(e+1)) its float grid is g = 2^(e-23) and RN_g(s + p) =
 // s + RN_g(p), so with q = s / g the chain is the integer sum q += I_k, I_k = RN_g(p_k) / g, which one
-// double addition p_k + 1.5 * 2^52 * g leaves in the low mantissa word. Which binade s is in when bin k
-// is added is PREDICTED from the exact prefix sum S_(k-1) of the p_k in double (the float chain stays
-// within 257 * 2^-25 relative of it): lane b owns bins 16 b + 1 .. 16 b + 16, a double prefix scan over the
-// half-warp gives S, every bin is converted ONCE at its predicted grid, and the bins at which the
-// predicted binade changes ("crossings", ~4 per hop) are added one after the other with the reference's
-// own double-add / float-convert step, the integer sums of the bins between them coming from an
-// integer prefix scan. Bins 0..16 (lane 0), where the sum climbs a binade per bin, run as the plain
-// chain meanwhile. Every prediction is VERIFIED on the way (the grid assumed for a run of bins is the
-// grid the chain really has; the sum stays below 2^24 grid units up to the next crossing); a hop that
-// fails (~6e-5 of random spectra: a prefix sum within rounding noise of a power of two) is redone by the
-// binade-by-binade scan above. Host model and test against the sequential chain: tools/chain_model.c.
-__device__ __forceinline__ double float_chain(double *xr, int lane16, bool active, bool force_slow) {
+// double addition p_k + 1.5 * 2^52 * g leaves in the low mantissa word. Which binade s is in when a bin
+// is added is PREDICTED from the exact prefix sum S of the p_k in double (the float chain stays within
+// 257 * 2^-25 relative of it): lane b owns bins 16 b + 1 .. 16 b + 16 in four groups of four, a double
+// prefix scan over the half-warp gives S at every group boundary. A group over which S keeps its exponent
+// is CLEAN: its bins are converted at that binade's grid and added as integers (an integer prefix scan
+// gives the sum of all clean bins in front of any group). The other groups (~3 per hop) are DIRTY: their
+// four bins are added one after the other, in order, with the reference's own double-add / float-convert
+// step. Bins 0..16 (lane 0), where the sum climbs a binade per bin, run as the plain chain meanwhile.
+// Every prediction is VERIFIED on the way: in front of a dirty group the integer sum is below 2^24 and
+// the chain is in the predicted binade, behind it the chain is in the binade predicted for the next
+// group, and the same at the end; clean neighbours share their boundary exponent by construction. A hop
+// that fails (a prefix sum within rounding noise of a power of two; sums that are not normal floats) is
+// redone by the binade-by-binade scan above. Host model and test against the sequential chain:
+// tools/chain_model4.c.
+__device__ __forceinline__ double float_chain(const double *xr, int lane16, bool active, bool force_slow) {
     const unsigned full = 0xffffffffu;
-    unsigned char *aux = reinterpret_cast<unsigned char *>(xr + 272);
+    const int hw = (threadIdx.x >> 4) & 1;
     double pv[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pv[i] = xr[17 * lane16 + 1 + i]; // bins 16 lane16 + 1 + i
-    // bins 0..16 one by one (independent of everything up to the resolution below)
+    load_row(xr, lane16, pv); // bins 16 lane16 + 1 + i
+    const double p0 = xr[15]; // bin 0
+    // bins 0..16 one by one on lane 0's registers (the other lanes run the same instructions on their own bins;
+    // only lane 0's result is used). Independent of everything up to the resolution below.
     double r16;
     {
-        float sf = 0.0f;
+        float sf = (float)p0;
 #pragma unroll
-        for (int k = 0; k <= 16; ++k) sf = (float)((double)sf + xr[k]);
+        for (int k = 0; k < 16; ++k) sf = (float)((double)sf + pv[k]);
         r16 = (double)sf;
     }
+    r16 = __shfl_sync(full, r16, 0, 16);
     // exact prefix sums in double: local, then across the half-warp
-    double c[16];
-    c[0] = pv[0] + (lane16 == 0 ? xr[0] : 0.0);
-#pragma unroll
-    for (int i = 1; i < 16; ++i) c[i] = c[i - 1] + pv[i];
-    double inc = c[15];
+    double c3, c7, c11, inc;
+    {
+        double c = pv[0] + (lane16 == 0 ? p0 : 0.0);
+        c += pv[1]; c += pv[2]; c += pv[3]; c3 = c;
+        c += pv[4]; c += pv[5]; c += pv[6]; c += pv[7]; c7 = c;
+        c += pv[8]; c += pv[9]; c += pv[10]; c += pv[11]; c11 = c;
+        c += pv[12]; c += pv[13]; c += pv[14]; c += pv[15];
+        inc = c;
+    }
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) {
         const double up = __shfl_up_sync(full, inc, o, 16);
@@ -271,75 +352,82 @@ __device__ __forceinline__ double float_chain(double *xr, int lane16, bool activ
     // chain ends at r16. (Without this a silent hop, whose sum never becomes a normal float, would take the
     // slow path one bin at a time.)
     const bool rest_zero = __shfl_sync(full, inc, 15, 16) == __shfl_sync(full, inc, 0, 16);
-    // every bin at its predicted grid; crossing bins and lane 0's bins (already in r16) count nothing
+    // the four groups: exponent of S at the boundaries, clean groups summed at their grid
     const bool mine = active && lane16 != 0;
-    int hprev = __double2hiint(excl);
-    unsigned acc = 0, mask = 0;
-    unsigned L[16], egw[8];
+    int h[5];
+    h[0] = __double2hiint(excl);
+    h[1] = __double2hiint(excl + c3);
+    h[2] = __double2hiint(excl + c7);
+    h[3] = __double2hiint(excl + c11);
+    h[4] = __double2hiint(inc);
+    unsigned before[4], pack[4], dirty = 0, run = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int hs = __double2hiint(excl + c[i]);
-        const int hiM = (hprev & 0x7FF00000) + 0x1D80000; // 1.5 * 2^(e + 29): ulp = float grid of binade e
-        const double t = pv[i] + __hiloint2double(hiM, 0);
-        const bool x = ((hs ^ hprev) & 0x7FF00000) != 0;
-        L[i] = acc;
-        acc += (x || !mine) ? 0u : (unsigned)__double2loint(t);
-        mask |= x ? (1u << i) : 0u;
-        if (i & 1) egw[i >> 1] = __byte_perm(egw[i >> 1], (unsigned)hprev, 0x7610); // high half <- top 16 bits
-        else egw[i >> 1] = (unsigned)hprev >> 16;
-        hprev = hs;
+    for (int j = 0; j < 4; ++j) {
+        const double M = __hiloint2double((h[j] & 0x7FF00000) + 0x1D80000, 0); // 1.5 * 2^(e + 29): ulp = float grid of binade e
+        unsigned g = 0;
+#pragma unroll
+        for (int i = 4 * j; i < 4 * j + 4; ++i) g += (unsigned)__double2loint(pv[i] + M);
+        const bool d = mine && (((h[j] ^ h[j + 1]) & 0x7FF00000) != 0);
+        before[j] = run;
+        run += (d || !mine) ? 0u : g;
+        dirty |= d ? (1u << j) : 0u;
+        pack[j] = ((unsigned)h[j] >> 20) | (((unsigned)h[j + 1] >> 20) << 16); // exponents in front of / behind the group
     }
-    if (!mine) mask = 0;
-    unsigned incI = acc;
+    unsigned incI = run;
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) {
         const unsigned up = __shfl_up_sync(full, incI, o, 16);
         if (lane16 >= o) incI += up;
     }
-    const unsigned baseI = incI - acc;
-#pragma unroll
-    for (int v4 = 0; v4 < 4; ++v4)
-        *reinterpret_cast<uint4 *>(aux + kAuxPb + 16 * (16 * v4 + lane16)) =
-            make_uint4(baseI + L[4 * v4], baseI + L[4 * v4 + 1], baseI + L[4 * v4 + 2], baseI + L[4 * v4 + 3]);
-#pragma unroll
-    for (int v4 = 0; v4 < 2; ++v4)
-        *reinterpret_cast<uint4 *>(aux + kAuxEg + 16 * (16 * v4 + lane16)) =
-            make_uint4(egw[4 * v4], egw[4 * v4 + 1], egw[4 * v4 + 2], egw[4 * v4 + 3]);
-    *reinterpret_cast<unsigned short *>(aux + kAuxMask + 2 * lane16) = (unsigned short)mask;
-    if (lane16 == 15) {
-        *reinterpret_cast<unsigned *>(aux + kAuxTot) = incI;
-        *reinterpret_cast<int *>(aux + kAuxEnd) = hprev >> 20;
+    const unsigned baseI = incI - run;
+    const unsigned total = __shfl_sync(full, incI, 15, 16);
+    const int e_end = __shfl_sync(full, h[4], 15, 16) >> 20;
+    // the dirty groups of this half-warp, bit 4 b + j, as two words (lanes 0..7, lanes 8..15)
+    unsigned m_lo, m_hi;
+    {
+        const unsigned bits = dirty << (4 * (lane16 & 7));
+        const int word = 2 * hw + (lane16 >> 3);
+        const unsigned w0 = __reduce_or_sync(full, word == 0 ? bits : 0u), w1 = __reduce_or_sync(full, word == 1 ? bits : 0u);
+        const unsigned w2 = __reduce_or_sync(full, word == 2 ? bits : 0u), w3 = __reduce_or_sync(full, word == 3 ? bits : 0u);
+        m_lo = hw ? w2 : w0;
+        m_hi = hw ? w3 : w1;
     }
-    __syncwarp(full);
-    // the crossings in order (no warp-wide operation in here: the two half-warps run their own count)
+    // the dirty groups in order; both half-warps step together (the one that runs out idles)
     int ex = (__double2hiint(r16) >> 20) & 0x7ff;
     unsigned q = (((unsigned)__double2hiint(r16) & 0xFFFFFu) << 3) | ((unsigned)__double2loint(r16) >> 29) | 0x800000u;
     bool ok = !active || (ex >= 1023 - 126 && ex <= 1023 + 126);
     unsigned Pprev = 0;
-    const uint4 m0 = *reinterpret_cast<const uint4 *>(aux + kAuxMask), m1 = *reinterpret_cast<const uint4 *>(aux + kAuxMask + 16);
-    const unsigned words[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        unsigned m = words[w];
-        while (m) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            const int b = 2 * w + (bit >> 4), i = bit & 15;
-            const unsigned Pbj = *reinterpret_cast<const unsigned *>(aux + kAuxPb + 16 * (16 * (i >> 2) + b) + 4 * (i & 3));
-            const unsigned eg16 = *reinterpret_cast<const unsigned short *>(aux + kAuxEg + 16 * (16 * (i >> 3) + b) + 2 * (i & 7));
-            const double pk = xr[17 * b + i + 1];
-            const unsigned qb = q + (Pbj - Pprev);
-            ok = ok && qb < (1u << 24) && (int)(eg16 >> 4) == ex;
-            const double sq = __hiloint2double((ex << 20) | (int)((qb & 0x7FFFFFu) >> 3), (int)((qb & 7u) << 29));
-            const double r = (double)(float)(sq + pk); // reference src/tempo_atk_sort.c:147
+    while (__any_sync(full, (m_lo | m_hi) != 0u)) {
+        const bool act = (m_lo | m_hi) != 0u;
+        const int bit = m_lo ? (__ffs(m_lo) - 1) : (m_hi ? 32 + (__ffs(m_hi) - 1) : 4); // idle: lane 1, group 0
+        if (m_lo) m_lo &= m_lo - 1;
+        else m_hi &= m_hi - 1;
+        const int b = bit >> 2, j = bit & 3;
+        const unsigned bsel = (j & 2) ? ((j & 1) ? before[3] : before[2]) : ((j & 1) ? before[1] : before[0]);
+        const unsigned psel = (j & 2) ? ((j & 1) ? pack[3] : pack[2]) : ((j & 1) ? pack[1] : pack[0]);
+        const unsigned Pb = __shfl_sync(full, baseI + bsel, b, 16);
+        const unsigned pk = __shfl_sync(full, psel, b, 16);
+        // the group's four bins (row b, elements 4 j .. 4 j + 3)
+        const double2 *row = reinterpret_cast<const double2 *>(xr + kPRow * b);
+        const double2 pa = row[2 * j], pb = row[2 * j + 1], pc = row[8];
+        const double p3 = (j == 3 && b <= 6) ? pc.y : pb.y;
+        if (act) {
+            const unsigned qb = q + (Pb - Pprev);
+            ok = ok && qb < (1u << 24) && (int)(pk & 0x7FFu) == ex;
+            double r = grid_to_double(ex, qb);
+            r = (double)(float)(r + pa.x); // reference src/tempo_atk_sort.c:147
+            r = (double)(float)(r + pa.y);
+            r = (double)(float)(r + pb.x);
+            r = (double)(float)(r + p3);
             ex = (__double2hiint(r) >> 20) & 0x7ff;
             q = (((unsigned)__double2hiint(r) & 0xFFFFFu) << 3) | ((unsigned)__double2loint(r) >> 29) | 0x800000u;
-            Pprev = Pbj;
+            ok = ok && (int)((pk >> 16) & 0x7FFu) == ex && ex <= 1023 + 126;
+            Pprev = Pb;
         }
     }
-    const unsigned qf = q + (*reinterpret_cast<const unsigned *>(aux + kAuxTot) - Pprev);
-    ok = ok && (!active || (qf < (1u << 24) && *reinterpret_cast<const int *>(aux + kAuxEnd) == ex && ex <= 1023 + 126));
-    double r = __hiloint2double((ex << 20) | (int)((qf & 0x7FFFFFu) >> 3), (int)((qf & 7u) << 29));
+    const unsigned qf = q + (total - Pprev);
+    ok = ok && (!active || (qf < (1u << 24) && e_end == ex && ex <= 1023 + 126));
+    double r = grid_to_double(ex, qf);
     if (rest_zero) { r = r16; ok = true; }
     if (__any_sync(full, !ok) || force_slow) r = float_chain_rounds(xr, lane16, active, r16);
     return r;
@@ -347,53 +435,51 @@ __device__ __forceinline__ double float_chain(double *xr, int lane16, bool activ
 
 } // namespace
 
-template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_kernel(EnvelopeParams p) {
+template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envelope_kernel(EnvelopeParams p) {
     using G = EG<DUP>;
     extern __shared__ __align__(128) unsigned char smem[];
     const SongDesc sd = p.songs[blockIdx.y];
-    if (blockIdx.x * kHopsPerCta >= sd.n_hops) return;
+    if (blockIdx.x * G::hops_per_cta >= sd.n_hops) return;
     const SongNorm nm = p.norm[blockIdx.y];
     if (nm.status != 0) return;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int hw = lane >> 4, lane16 = lane & 15; // half-warp = hop of the pair
-    double *tab = reinterpret_cast<double *>(smem + G::off_tab);
+    int *tabi = reinterpret_cast<int *>(smem + G::off_tabi);
+    double *tabd = reinterpret_cast<double *>(smem + G::off_tabd);
     // Head table: a window's output t (its first 16) lacks the terms of the `pre` raw samples X[0..pre)
-    // in front of the window; row `lane16` holds the coefficients of those terms for the output this
-    // lane corrects, then the sum of the dropped coefficients (for the mean term).
+    // in front of the window; row `lane16` holds the integer coefficients of those terms for the output this
+    // lane corrects, tabd the sum of the dropped coefficients (for the mean term).
     //   DUP: lane = n + 8 part, output 2 n + part: sum_{j >= n} fold(8 + n - j) X[j]
     //   else: lane = output j:                      sum_{i >= j} c(j + 16 - i) X[i]
     if (tid < 16) {
-        double *trow = tab + tid * G::row;
+        int *trow = tabi + tid * G::taps;
         double dsum = 0.0;
         if (DUP) {
             const int n = tid & 7, part = tid >> 3;
             for (int j = 0; j < 8; ++j) {
                 const int m = 8 + n - j;
-                const double c = (j >= n) ? (part ? fold_d_rt(m) : fold_e_rt(m)) : 0.0;
-                trow[j] = c;
-                dsum += c;
+                trow[j] = (j >= n) ? (part ? fold_d_i_rt(m) : fold_e_i_rt(m)) : 0;
+                dsum += (j >= n) ? (part ? fold_d_d_rt(m) : fold_e_d_rt(m)) : 0.0;
             }
         } else {
             for (int i = 0; i < 16; ++i) {
-                const double c = (i >= tid) ? fir_coef_rt(tid + 16 - i) : 0.0;
-                trow[i] = c;
-                dsum += c;
+                trow[i] = (i >= tid) ? lag_i_rt(tid + 16 - i) : 0;
+                dsum += (i >= tid) ? lag_d_rt(tid + 16 - i) : 0.0;
             }
         }
-        trow[G::taps] = dsum;
-        trow[G::taps + 1] = 0.0;
+        tabd[tid] = dsum;
     }
 
     unsigned char *wsm = smem + warp * G::w_bytes;
     double2 *xchg = reinterpret_cast<double2 *>(wsm + G::w_xchg) + hw * kXchgElems;
-    unsigned char *newblk = wsm + G::w_xchg; // FIR blocks B + 1, B + 2 of the pair (consumed before the FFT exchange)
-    unsigned char *carry = wsm + G::w_carry; // FIR block B
+    unsigned char *newblk = wsm + G::w_xchg; // FIR block B + 1 of the pair (consumed before the FFT exchange)
+    unsigned char *carry = wsm + G::w_carry; // FIR block B, overwritten with block B + 2 once hop 0 holds B in registers
     unsigned char *raw = wsm + G::w_raw;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + G::w_bar);
 
-    const int B0 = blockIdx.x * kHopsPerCta + warp * (2 * kPairsPerWarp); // first hop (= first block) of this warp
+    const int B0 = blockIdx.x * G::hops_per_cta + warp * (2 * kPairsPerWarp); // first hop (= first block) of this warp
     const int n_mine = min(2 * kPairsPerWarp, sd.n_hops - B0);            // hops of this warp
     const int n_pairs = (n_mine + 1) >> 1;
     const short *stream = p.stream + (DUP ? sd.q_off : sd.pcm_off);
@@ -434,16 +520,14 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
     __syncthreads(); // the only block-wide barrier: table and mbarriers are set up
     if (n_mine <= 0) return;
 
-    // x = (s / 32768 - mean_d) / var_d (reference src/tempo_atk_sort.c:110-113) is affine in the raw
-    // sample s, and the FIR is linear: y = A * (sum c_k s_k) - Bm * (sum c_k), A = 1 / (32768 var_d),
-    // Bm = mean_d / var_d. The taps run over exact integers; one FMA per output normalises.
-    // Both carry an extra factor 1/2 (exact): it is the 1/2 of the real-FFT even/odd split, so the split
-    // below produces X_k without its 0.25 |.|^2 scaling step; the three purely real bins are scaled back.
-    const double A = nm.inv_var_d * (1.0 / 32768) * 0.5;
+    // y = A7 * (sum C_k s_k) - Bm * (sum c_k) (header comment). Both carry an extra factor 1/2 (exact): it is
+    // the 1/2 of the real-FFT even/odd split, so the split below produces X_k without its 0.25 |.|^2 scaling
+    // step; the three purely real bins are scaled back.
+    const double A7 = nm.inv_var_d * (1.0 / 32768) * 0.5 * 1e-7;
     const double Bm = nm.mean_d * nm.inv_var_d * 0.5;
-    double csum_all = fir_tap(8);
+    double csum_all = c_fir_half[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) csum_all += 2.0 * fir_tap(k);
+    for (int k = 0; k < 8; ++k) csum_all += 2.0 * c_fir_half[k];
     const double Ball = Bm * csum_all;
     const unsigned full = 0xffffffffu;
     const int key = 16 * (lane16 & 7);
@@ -451,81 +535,112 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
     int coff[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) coff[i] = 16 * (lane16 ^ ((2 * i + (lane16 >> 3)) & 7));
+    // the head correction's own constants
+    const double head_mean = Bm * tabd[lane16];
 
     for (int q = -1; q < n_pairs; ++q) {
         const unsigned char *rcur = raw + (q & 1) * G::raw_bytes;
+        double2 v[16];
+        // ---- hop 0 takes block B out of the carry slot before the upper half-warp overwrites it with B + 2
+        if (q >= 0 && hw == 0) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) v[a] = *reinterpret_cast<const double2 *>(carry + 256 * a + coff[a & 3]);
+        }
         mbar_wait(bar + (q & 1), (unsigned)((q + 1) >> 1) & 1u);
+        __syncwarp(full);
 
         // ---- continuous FIR: half-warp hw computes block B + 1 + hw, every lane 16 consecutive outputs
         // (8 cells); in the prologue only the upper half-warp's block (B0) is kept
         {
             const unsigned char *sp = rcur + lane * (G::per_thread * 2); // r[per_thread * lane ...]
-            double yo[16];
+            unsigned char *slot = (hw ? carry : newblk) + 128 * lane16;
+            const bool keep = q >= 0 || hw == 1;
             if (DUP) {
                 // inputs u[k] = r[8 lane + k], k = 0..15; output pair o uses u[8 + o - m], m = 0..8
                 const int4 u0 = reinterpret_cast<const int4 *>(sp)[0], u1 = reinterpret_cast<const int4 *>(sp)[1];
                 const int wds[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-                double u[16];
+                int u[16];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    u[2 * i] = (double)(short)(wds[i] & 0xffff);
-                    u[2 * i + 1] = (double)(short)(wds[i] >> 16);
+                    u[2 * i] = (int)(short)(wds[i] & 0xffff);
+                    u[2 * i + 1] = wds[i] >> 16;
                 }
+#if BLX_ENV_FIR_INT
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
-                    double ye = fold_e(0) * u[8 + o];
-                    double yd = fold_d(0) * u[8 + o];
+                    long long ye = 0, yd = 0;
+                    fir_dup_taps<0>(u, o, ye, yd);
+                    const double2 y2 = make_double2(fma(i64_to_double(ye), A7, -Ball), fma(i64_to_double(yd), A7, -Ball));
+                    if (keep) *reinterpret_cast<double2 *>(slot + ((16 * o) ^ key)) = y2;
+                }
+#else
+                double ud[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ud[i] = (double)u[i];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    double ye = (double)fold_e_i(0) * ud[8 + o], yd = (double)fold_d_i(0) * ud[8 + o];
 #pragma unroll
                     for (int m = 1; m <= 8; ++m) {
-                        ye = fma(fold_e(m), u[8 + o - m], ye);
-                        yd = fma(fold_d(m), u[8 + o - m], yd);
+                        ye = fma((double)fold_e_i(m), ud[8 + o - m], ye);
+                        yd = fma((double)fold_d_i(m), ud[8 + o - m], yd);
                     }
-                    yo[2 * o] = fma(ye, A, -Ball);
-                    yo[2 * o + 1] = fma(yd, A, -Ball);
+                    const double2 y2 = make_double2(fma(ye, A7, -Ball), fma(yd, A7, -Ball));
+                    if (keep) *reinterpret_cast<double2 *>(slot + ((16 * o) ^ key)) = y2;
                 }
+#endif
             } else {
-                // inputs xv[k] = r[16 lane + k], k = 0..31; output o uses xv[o + 16 - m], m = 0..16, summed in
-                // the reference's order (reference src/tempo_atk_sort.c:124-137)
-                double xv[32];
+                // inputs xv[k] = r[16 lane + k], k = 0..31; output o uses xv[o + 16 - m], m = 0..16
+                // (reference src/tempo_atk_sort.c:124-137; exact, so the order of the sum is free)
+                int xv[32];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int4 q4 = reinterpret_cast<const int4 *>(sp)[i];
                     const int wds[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        xv[8 * i + 2 * j] = (double)(short)(wds[j] & 0xffff);
-                        xv[8 * i + 2 * j + 1] = (double)(short)(wds[j] >> 16);
+                        xv[8 * i + 2 * j] = (int)(short)(wds[j] & 0xffff);
+                        xv[8 * i + 2 * j + 1] = wds[j] >> 16;
                     }
                 }
+#if !BLX_ENV_FIR_INT
+                double xd[32];
 #pragma unroll
-                for (int o = 0; o < 16; ++o) {
-                    double y = 0;
+                for (int i = 0; i < 32; ++i) xd[i] = (double)xv[i];
+#endif
 #pragma unroll
-                    for (int k = 7; k >= 1; --k) y += fir_tap(k) * (xv[o + 16 - k] + xv[o + k]);
-                    y += xv[o + 8] * fir_tap(8);
-                    y += fir_tap(0) * (xv[o + 16] + xv[o]);
-                    yo[o] = fma(y, A, -Ball);
+                for (int o2 = 0; o2 < 8; ++o2) {
+                    double yy[2];
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int o = 2 * o2 + t;
+#if BLX_ENV_FIR_INT
+                        long long y = madw<tap_i(8)>(xv[o + 8], 0ll);
+                        fir_sym_taps<0>(xv, o, y);
+                        yy[t] = fma(i64_to_double(y), A7, -Ball);
+#else
+                        double y = (double)tap_i(8) * xd[o + 8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) y = fma((double)tap_i(k), xd[o + 16 - k] + xd[o + k], y);
+                        yy[t] = fma(y, A7, -Ball);
+#endif
+                    }
+                    if (keep) *reinterpret_cast<double2 *>(slot + ((16 * o2) ^ key)) = make_double2(yy[0], yy[1]);
                 }
-            }
-            unsigned char *slot = ((q < 0) ? carry : newblk + hw * kSlotBytes) + 128 * lane16;
-            if (q >= 0 || hw == 1) {
-#pragma unroll
-                for (int m = 0; m < 8; ++m)
-                    *reinterpret_cast<double2 *>(slot + ((16 * m) ^ key)) = make_double2(yo[2 * m], yo[2 * m + 1]);
             }
         }
         __syncwarp(full);
         if (q < 0) continue;
 
-        // ---- FFT input: the 512 FIR outputs of this half-warp's window: blocks B, B + 1 (hop 0) or
-        // B + 1, B + 2 (hop 1) ...
-        double2 v[16];
+        // ---- FFT input: the 512 FIR outputs of this half-warp's window: blocks B, B + 1 (hop 0, B already in
+        // registers) or B + 1, B + 2 (hop 1) ...
         {
-            const unsigned char *ba = hw ? newblk : carry, *bb = newblk + hw * kSlotBytes;
+            const unsigned char *upper = hw ? carry : newblk; // second block of the window: B + 2 / B + 1
 #pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                v[a] = *reinterpret_cast<const double2 *>(ba + 256 * a + coff[a & 3]);
-                v[a + 8] = *reinterpret_cast<const double2 *>(bb + 256 * a + coff[a & 3]);
+            for (int a = 0; a < 8; ++a) v[a + 8] = *reinterpret_cast<const double2 *>(upper + 256 * a + coff[a & 3]);
+            if (hw) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) v[a] = *reinterpret_cast<const double2 *>(newblk + 256 * a + coff[a & 3]);
             }
         }
         // ... whose first 16 see an empty delay line: take out the terms of the raw samples in front of
@@ -533,36 +648,28 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
         // window starts at r[pre]; hop 0's one block earlier, at r'[blk + pre] of the previous pass.
         {
             const unsigned char *hp = hw ? rcur : raw + ((q & 1) ^ 1) * G::raw_bytes + G::blk_bytes;
-            const double *trow = tab + lane16 * G::row;
-            double X[G::taps];
+            const int4 *trow = reinterpret_cast<const int4 *>(tabi + lane16 * G::taps);
+            long long corr = 0;
 #pragma unroll
             for (int i = 0; i < G::taps / 8; ++i) {
                 const int4 q4 = reinterpret_cast<const int4 *>(hp)[i];
-                const int wds[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    X[8 * i + 2 * j] = (double)(short)(wds[j] & 0xffff);
-                    X[8 * i + 2 * j + 1] = (double)(short)(wds[j] >> 16);
-                }
+                const int4 ca = trow[2 * i], cb = trow[2 * i + 1];
+                corr = madw_r((int)(short)(q4.x & 0xffff), ca.x, corr);
+                corr = madw_r(q4.x >> 16, ca.y, corr);
+                corr = madw_r((int)(short)(q4.y & 0xffff), ca.z, corr);
+                corr = madw_r(q4.y >> 16, ca.w, corr);
+                corr = madw_r((int)(short)(q4.z & 0xffff), cb.x, corr);
+                corr = madw_r(q4.z >> 16, cb.y, corr);
+                corr = madw_r((int)(short)(q4.w & 0xffff), cb.z, corr);
+                corr = madw_r(q4.w >> 16, cb.w, corr);
             }
-            double corr = 0.0;
-#pragma unroll
-            for (int i = 0; i < G::taps; i += 2) {
-                const double2 c2 = *reinterpret_cast<const double2 *>(trow + i);
-                corr = fma(c2.x, X[i], corr);
-                corr = fma(c2.y, X[i + 1], corr);
-            }
-            const double h = fma(Bm, trow[G::taps], -(A * corr));
+            const double h = fma(-A7, i64_to_double(corr), head_mean);
             const int s0 = DUP ? lane16 : 2 * lane16, s1 = DUP ? lane16 + 8 : 2 * lane16 + 1;
             const double h0 = __shfl_sync(full, h, s0 & 15, 16);
             const double h1 = __shfl_sync(full, h, s1 & 15, 16);
             if (lane16 < 8) { v[0].x += h0; v[0].y += h1; }
         }
         __syncwarp(full); // FIR blocks and raw samples are consumed
-        if (hw == 1) { // block B + 2 (this half-warp's second block) becomes the next pair's block B
-#pragma unroll
-            for (int a = 0; a < 8; ++a) *reinterpret_cast<double2 *>(carry + 256 * a + coff[a & 3]) = v[a + 8];
-        }
         if (lane == 0 && q + 1 < n_pairs) issue_pass(q + 1);
 
         // ---- 2 x (512-point double real FFT + float-accumulated power), one hop per half-warp in
@@ -580,15 +687,18 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
 #pragma unroll
             for (int d = 0; d < 8; ++d) Bz[d] = xchg[(256 - (lane16 + 16 * d)) & 255];
             __syncwarp(full);
-            double *xr = reinterpret_cast<double *>(xchg); // |X_k|^2, k = 0..256, at pbin(k)
+            double *xr = reinterpret_cast<double *>(xchg); // |X_k|^2, k = 0..256, at pidx(k)
+            // bins k = lane16 + 16 d and 256 - k: rows d and 15 - d (lane 0: the last element of rows d - 1 and 15 - d)
+            const int ia0 = (lane16 == 0) ? -1 : lane16 - 1; // slot of bin k in row d; lane 0: see below
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 const int k = lane16 + 16 * d;
                 const double2 Zk = v[fft16_reg_of(d)];
+                double pa, pb;
                 if (k == 0) {
                     const double x0 = Zk.x + Zk.y, xn = Zk.x - Zk.y; // X_0 and X_256 are real
-                    xr[pbin(0)] = 4.0 * (x0 * x0);
-                    xr[pbin(256)] = 4.0 * (xn * xn);
+                    pa = 4.0 * (x0 * x0);
+                    pb = 4.0 * (xn * xn);
                 } else {
                     const double2 wk = p.tw2[k];
                     const double sr = Zk.x + Bz[d].x, si = Zk.y - Bz[d].y;
@@ -597,19 +707,25 @@ template <bool DUP> __global__ void __launch_bounds__(kEnvThreads, 2) envelope_k
                     const double ti = dr * wk.y + di * wk.x;
                     const double ar = sr + ti, ai = si - tr;
                     const double cr = sr - ti, ci = si + tr;
-                    xr[pbin(k)] = ar * ar + ai * ai;
-                    xr[pbin(256 - k)] = cr * cr + ci * ci;
+                    pa = ar * ar + ai * ai;
+                    pb = cr * cr + ci * ci;
                 }
+                // bin k: lanes 1..15 -> row d slot lane16 - 1; lane 0 -> bin 16 d = last element of row d - 1 (bin 0: slot 15 of row 0)
+                const int ja = (lane16 != 0) ? kPRow * d + ia0 : (d == 0 ? 15 : kPRow * (d - 1) + pslot15(d - 1));
+                // bin 256 - k: lanes 1..15 -> row 15 - d slot 15 - lane16; lane 0 -> bin 16 (16 - d) = last element of row 15 - d
+                const int jb = kPRow * (15 - d) + ((lane16 != 0) ? 15 - lane16 : pslot15(15 - d));
+                xr[ja] = pa;
+                xr[jb] = pb;
             }
             if (lane16 == 0) {
                 const double2 Zk = v[fft16_reg_of(8)];
-                xr[pbin(128)] = 4.0 * (Zk.x * Zk.x + Zk.y * Zk.y);
+                xr[pidx(128)] = 4.0 * (Zk.x * Zk.x + Zk.y * Zk.y);
             }
             __syncwarp(full);
             const double e = float_chain(xr, lane16, active, p.slow_chain != 0);
             if (active && lane16 == 0) p.energy[sd.env_off + hop] = e;
         }
-        __syncwarp(full); // the exchange buffers are free for the next pair's FIR blocks
+        __syncwarp(full); // the exchange buffers are free for the next pair's FIR block
     }
 }
 
@@ -622,9 +738,13 @@ cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, 
         if (e != cudaSuccess) return e;
     }
     if (max_hops <= 0) return cudaSuccess;
-    dim3 grid((unsigned)((max_hops + kHopsPerCta - 1) / kHopsPerCta), (unsigned)n_songs);
-    if (p.dup) envelope_kernel<true><<<grid, kEnvThreads, EG<true>::bytes, st>>>(p);
-    else envelope_kernel<false><<<grid, kEnvThreads, EG<false>::bytes, st>>>(p);
+    if (p.dup) {
+        dim3 grid((unsigned)((max_hops + EG<true>::hops_per_cta - 1) / EG<true>::hops_per_cta), (unsigned)n_songs);
+        envelope_kernel<true><<<grid, EG<true>::threads, EG<true>::bytes, st>>>(p);
+    } else {
+        dim3 grid((unsigned)((max_hops + EG<false>::hops_per_cta - 1) / EG<false>::hops_per_cta), (unsigned)n_songs);
+        envelope_kernel<false><<<grid, EG<false>::threads, EG<false>::bytes, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

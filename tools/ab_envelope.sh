@@ -1,0 +1,38 @@
+#!/bin/bash
+# Builds variants of libbliss.so that differ in the envelope kernel's build-time switches (on the CPU box, before
+# gpurun) or times them (on the GPU box): tools/ab_envelope.sh build | run [songs]
+# Variants live in tools/variants/ (git-ignored, shipped by gpurun).
+set -e
+cd "$(dirname "$0")/.."
+VAR=tools/variants
+declare -A FLAGS=(
+  [int8]="-DBLX_ENV_FIR_INT=1 -DBLX_ENV_WARPS=8"
+  [fp8]="-DBLX_ENV_FIR_INT=0 -DBLX_ENV_WARPS=8"
+  [int9]="-DBLX_ENV_FIR_INT=1 -DBLX_ENV_WARPS=9"
+  [fp9]="-DBLX_ENV_FIR_INT=0 -DBLX_ENV_WARPS=9"
+)
+if [ "$1" = build ]; then
+  mkdir -p $VAR
+  make -C bliss_b200 -j8 >/dev/null
+  for v in "${!FLAGS[@]}"; do
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC ${FLAGS[$v]} $EXTRA -Xptxas -v \
+      -c bliss_b200/csrc/envelope.cu -o $VAR/envelope_$v.o 2> $VAR/ptxas_$v.txt
+    objs=$(ls bliss_b200/csrc/*.o bliss_b200/host/*.o | grep -v csrc/envelope.o)
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $VAR/libbliss_$v.so $objs $VAR/envelope_$v.o -lpthread -lm
+    echo "$v: $(grep -A1 'envelope_kernelILb1' $VAR/ptxas_$v.txt | grep -o 'bytes spill stores' | head -1) $(grep -A2 'envelope_kernelILb1' $VAR/ptxas_$v.txt | grep -o 'Used [0-9]* registers' | head -1)"
+  done
+else
+  songs=${2:-1024}
+  for so in $VAR/libbliss_*.so; do
+    v=$(basename $so .so)
+    BLISS_B200_LIB=$PWD/$so python bench.py --steps 3 --warmup 2 --songs-per-step $songs --no-cpu --no-spectral --no-distance \
+      --e2e-songs 2 --s16-songs 128 --parity-songs 0 --chain-songs 0 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || echo "$v FAILED"
+    python - "$v" gpurun_out/ab_$v.json <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+k = d["roofline_kernels"]
+print("%-18s env %.3f ms  pass1 %.3f  step %.2f ms  native_s16 %.0f songs/s" % (sys.argv[1], k["envelope_kernel"]["ms_per_launch"],
+      k["pass1_kernel"]["ms_per_launch"], d["ms_per_step"], d["native_s16"]["value"] if d.get("native_s16") else 0))
+PY
+  done
+fi
