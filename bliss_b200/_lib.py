@@ -56,8 +56,9 @@ BLISS_H_SYMBOLS = [
     "bl_version", "bl_initialize_song", "bl_mean", "bl_variance", "bl_rectangular_filter",
 ]
 BLX_H_SYMBOLS = [
-    "blx_device_count", "blx_init", "blx_shutdown", "blx_last_error", "blx_configure", "blx_debug_flags",
-    "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_device", "blx_spectral_device",
+    "blx_device_count", "blx_init", "blx_shutdown", "blx_last_error", "blx_configure", "blx_configure_sub_batch", "blx_debug_flags",
+    "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_device", "blx_analyze_device_async", "blx_join",
+    "blx_spectral_device",
     "blx_distance_matrix", "blx_cosine_matrix", "blx_distance_rows_device", "blx_distance_nearest_device",
     "blx_mean_variance_s16", "blx_rectangular_filter", "blx_frontend_f32", "blx_envelope_energy_s16",
     "blx_frequency_spectrum_s16", "blx_histogram_s16", "blx_envelope_tail", "blx_envelope_energy_f32",
@@ -87,6 +88,8 @@ def load():
     L.blx_last_error.restype = ctypes.c_char_p
     L.blx_configure.restype = ctypes.c_int
     L.blx_configure.argtypes = [vp, ctypes.c_size_t]
+    L.blx_configure_sub_batch.restype = ctypes.c_int
+    L.blx_configure_sub_batch.argtypes = [vp, ctypes.c_int]
     L.blx_debug_flags.restype = ctypes.c_int
     L.blx_debug_flags.argtypes = [vp, ctypes.c_uint]
     L.blx_analyze_batch_s16.restype = ctypes.c_int
@@ -98,6 +101,10 @@ def load():
     L.blx_analyze_device.restype = ctypes.c_int
     L.blx_analyze_device.argtypes = [vp, ctypes.c_int, vp, c_i64p, c_i64p, c_i32p, c_u64p, ctypes.c_int,
                                      ctypes.c_uint, vp, vp]
+    L.blx_analyze_device_async.restype = ctypes.c_int
+    L.blx_analyze_device_async.argtypes = L.blx_analyze_device.argtypes
+    L.blx_join.restype = ctypes.c_int
+    L.blx_join.argtypes = [vp, vp]
     L.blx_spectral_device.restype = ctypes.c_int
     L.blx_spectral_device.argtypes = [vp, ctypes.c_int, vp, c_i64p, c_i64p, c_i32p, ctypes.c_int, vp, vp]
     for name in ("blx_distance_matrix", "blx_cosine_matrix"):

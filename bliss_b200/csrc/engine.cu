@@ -64,7 +64,7 @@ struct Slot {
     size_t h_songs_cap = 0;
     blx_result *h_results = nullptr; // pinned
     size_t h_results_cap = 0;
-    cudaEvent_t copied = nullptr, done = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr, env_done = nullptr;
     bool busy = false;
     int n_songs = 0;
     int first_song = 0; // index in the caller's batch
@@ -77,11 +77,17 @@ struct ProfRec {
 
 struct blx_engine {
     int device = 0;
-    cudaStream_t compute = nullptr, copy = nullptr;
+    // compute: pass 1, epilogue, envelope (and everything else); tail: log compression + the sequential tail of a
+    // (sub-)batch at high priority, so that its few CTAs slip in between the envelope CTAs of the next one
+    cudaStream_t compute = nullptr, copy = nullptr, tail = nullptr;
+    cudaEvent_t fence = nullptr, joined_work = nullptr, joined_tail = nullptr;
+    int sub_batch = 512;  // songs per kernel sequence of the device-resident entry points
+    int next_dev_slot = 0;
     float *d_hann = nullptr;
     float2 *d_tw1f = nullptr, *d_tw2f = nullptr;
     double2 *d_tw1d = nullptr, *d_tw2d = nullptr;
-    Slot slot[2];
+    static constexpr int kSlots = 4; // sub-batches in flight (the host-buffer path alternates between the first two)
+    Slot slot[kSlots];
     int next_slot = 0;
     size_t chunk_bytes = (size_t)1 << 30;
     unsigned debug = 0;
@@ -195,12 +201,20 @@ extern "C" int blx_init(int device, blx_engine **out) {
                     prop.minor);
     blx_engine *e = new blx_engine();
     e->device = device;
-    CK(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&e->compute, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&e->copy, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&e->tail, cudaStreamNonBlocking, prio_hi));
+    CK(cudaEventCreateWithFlags(&e->fence, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->joined_work, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->joined_tail, cudaEventDisableTiming));
+    for (int i = 0; i < blx_engine::kSlots; ++i) {
         CK(cudaEventCreateWithFlags(&e->slot[i].copied, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->slot[i].env_done, cudaEventDisableTiming));
     }
+    if (const char *sb = getenv("BLX_SUB_BATCH")) e->sub_batch = std::max(1, atoi(sb));
     // constant tables, computed once in double on the host
     std::vector<float> hann(kWin);
     for (int i = 0; i < kWin; ++i) // reference src/frequency_sort.c:40-42
@@ -236,7 +250,7 @@ extern "C" void blx_shutdown(blx_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < blx_engine::kSlots; ++i) {
         Slot &s = e->slot[i];
         s.pcm.release(); s.songs.release(); s.partials.release(); s.hist.release(); s.stats.release();
         s.norm.release(); s.energy.release(); s.xlog.release(); s.q.release(); s.results.release(); s.freq.release();
@@ -244,7 +258,12 @@ extern "C" void blx_shutdown(blx_engine *e) {
         if (s.h_results) cudaFreeHost(s.h_results);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.env_done) cudaEventDestroy(s.env_done);
     }
+    if (e->fence) cudaEventDestroy(e->fence);
+    if (e->joined_work) cudaEventDestroy(e->joined_work);
+    if (e->joined_tail) cudaEventDestroy(e->joined_tail);
+    if (e->tail) cudaStreamDestroy(e->tail);
     e->scratch_a.release();
     e->scratch_b.release();
     e->scratch_near.release();
@@ -260,6 +279,13 @@ extern "C" int blx_configure(blx_engine *e, size_t chunk_bytes) {
     if (!e) return fail(BLX_ERR_ARG, "null engine");
     if (chunk_bytes < ((size_t)1 << 20)) return fail(BLX_ERR_ARG, "chunk_bytes must be at least 1 MiB");
     e->chunk_bytes = chunk_bytes;
+    return BLX_OK;
+}
+
+extern "C" int blx_configure_sub_batch(blx_engine *e, int songs) {
+    if (!e) return fail(BLX_ERR_ARG, "null engine");
+    if (songs < 1) return fail(BLX_ERR_ARG, "sub-batch must be at least one song");
+    e->sub_batch = songs;
     return BLX_OK;
 }
 
@@ -358,8 +384,10 @@ static int ensure_host_songs(Slot &s, int n) {
 // The descriptors are uploaded here unless the caller already queued that copy (host-buffer path: behind the
 // chunk's PCM on the copy stream - a small host->device copy on the compute stream would wait in the copy
 // engine behind the NEXT chunk's PCM and stall this chunk's kernels for a whole chunk copy).
+// st: pass 1, epilogue, envelope; st_tail: log compression + tail (may be the same stream). The caller records the
+// chunk's completion on st_tail (st for the spectral-only form).
 static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *d_pcm, int n, unsigned what,
-                     blx_result *d_out, float *d_freq_only, cudaStream_t st, bool songs_uploaded = false) {
+                     blx_result *d_out, float *d_freq_only, cudaStream_t st, cudaStream_t st_tail, bool songs_uploaded = false) {
     const bool full = (d_freq_only == nullptr);
     CK(s.songs.reserve((size_t)n * sizeof(SongDesc)));
     CK(s.partials.reserve((size_t)std::max(plan.parts_total, 1) * 256 * sizeof(float)));
@@ -421,9 +449,13 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         ProfScope ps(e, BLX_K_ENVELOPE, st);
         CK(launch_envelope(p, plan.max_hops, n, st));
     }
+    if (st_tail != st) {
+        CK(cudaEventRecord(s.env_done, st));
+        CK(cudaStreamWaitEvent(st_tail, s.env_done, 0));
+    }
     if (what & BLX_DO_ENVELOPE) {
-        ProfScope ps(e, BLX_K_TAIL, st);
-        CK(launch_logcomp(static_cast<const double *>(s.energy.p), static_cast<double *>(s.xlog.p), plan.energy_total, st));
+        ProfScope ps(e, BLX_K_TAIL, st_tail);
+        CK(launch_logcomp(static_cast<const double *>(s.energy.p), static_cast<double *>(s.xlog.p), plan.energy_total, st_tail));
     }
     {
         TailParams p;
@@ -432,8 +464,8 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         p.xlog = static_cast<const double *>(s.xlog.p);
         p.out = d_out;
         p.what = what;
-        ProfScope ps(e, BLX_K_TAIL, st);
-        CK(launch_tail(p, n, st));
+        ProfScope ps(e, BLX_K_TAIL, st_tail);
+        CK(launch_tail(p, n, st_tail));
     }
     return BLX_OK;
 }
@@ -445,26 +477,48 @@ static int check_engine(blx_engine *e) {
 }
 
 // ---------------------------------------------------------------- device-resident entry points
+// The songs are analysed in sub-batches of e->sub_batch songs, each with its own intermediates (slot): pass 1,
+// epilogue and envelope of all sub-batches go to the engine's compute stream in order, the latency-bound tail of a
+// sub-batch (4 ms whatever its size) to the high-priority tail stream, where it runs under the next sub-batch's
+// kernels. `stream` is fenced in front (the engine's streams wait for it) and, unless `async`, behind (it waits for
+// the engine's streams): the caller sees ordinary stream semantics.
+static int join_stream(blx_engine *e, cudaStream_t st) {
+    CK(cudaEventRecord(e->joined_work, e->compute));
+    CK(cudaEventRecord(e->joined_tail, e->tail));
+    if (st != e->compute) CK(cudaStreamWaitEvent(st, e->joined_work, 0));
+    CK(cudaStreamWaitEvent(st, e->joined_tail, 0));
+    return BLX_OK;
+}
+
 static int analyze_device_impl(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets, const int64_t *lengths,
                                const int *channels, const uint64_t *duration_s, int n_songs, unsigned what,
-                               blx_result *d_out, float *d_freq_only, void *stream) {
+                               blx_result *d_out, float *d_freq_only, void *stream, bool async) {
     int rc = check_engine(e);
     if (rc) return rc;
     if (n_songs <= 0) return BLX_OK;
     if (!d_pcm || !offsets || !lengths) return fail(BLX_ERR_ARG, "null input array");
     if (fmt != BLX_FMT_S16 && fmt != BLX_FMT_F32) return fail(BLX_ERR_ARG, "unknown format %d", fmt);
     if (!(what & BLX_DO_ALL)) return fail(BLX_ERR_ARG, "empty analyser mask");
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->compute;
-    // songs are processed in runs of equal channel count, at most 65535 per launch (gridDim.y)
+    cudaStream_t user = stream ? static_cast<cudaStream_t>(stream) : e->compute;
+    const bool spectral = d_freq_only != nullptr;
+    // the spectral-only form (two kernels, no tail) runs on the caller's stream itself
+    cudaStream_t work = spectral ? user : e->compute;
+    if (user != work) {
+        CK(cudaEventRecord(e->fence, user));
+        CK(cudaStreamWaitEvent(work, e->fence, 0));
+    }
+    // the spectral-only form has no tail: one sequence per run of songs, all on the compute stream
+    const int sub = spectral ? 65535 : std::min(e->sub_batch, 65535);
+    // songs are processed in runs of equal channel count
     int i0 = 0;
     while (i0 < n_songs) {
         const int ch0 = (fmt == BLX_FMT_S16 && channels) ? channels[i0] : 2;
         int i1 = i0;
-        while (i1 < n_songs && i1 - i0 < 65535 && ((fmt == BLX_FMT_S16 && channels) ? channels[i1] : 2) == ch0) ++i1;
+        while (i1 < n_songs && i1 - i0 < sub && ((fmt == BLX_FMT_S16 && channels) ? channels[i1] : 2) == ch0) ++i1;
         if (fmt == BLX_FMT_S16 && ch0 != 1 && ch0 != 2) return fail(BLX_ERR_ARG, "song %d: %d channels unsupported", i0, ch0);
         const int n = i1 - i0;
-        Slot &s = e->slot[e->next_slot];
-        e->next_slot ^= 1;
+        Slot &s = e->slot[e->next_dev_slot];
+        e->next_dev_slot = (e->next_dev_slot + 1) % blx_engine::kSlots;
         if (s.busy) {
             CK(cudaEventSynchronize(s.done));
             s.busy = false;
@@ -479,13 +533,15 @@ static int analyze_device_impl(blx_engine *e, int fmt, const void *d_pcm, const 
         plan_songs(fmt, reinterpret_cast<const long long *>(offsets + i0), reinterpret_cast<const long long *>(lengths + i0),
                    ch0 == 1 ? kInS16Mono : kInS16Stereo,
                    duration_s ? reinterpret_cast<const unsigned long long *>(duration_s + i0) : nullptr, n, s.h_songs, &plan,
-                   d_freq_only != nullptr);
-        rc = run_chunk(e, s, plan, d_pcm, n, what, d_out ? d_out + i0 : nullptr, d_freq_only ? d_freq_only + i0 : nullptr, st);
+                   spectral);
+        rc = run_chunk(e, s, plan, d_pcm, n, what, d_out ? d_out + i0 : nullptr, d_freq_only ? d_freq_only + i0 : nullptr,
+                       work, spectral ? work : e->tail);
         if (rc) return rc;
-        CK(cudaEventRecord(s.done, st));
+        CK(cudaEventRecord(s.done, spectral ? work : e->tail));
         s.busy = true;
         i0 = i1;
     }
+    if (!async && !spectral) return join_stream(e, user);
     return BLX_OK;
 }
 
@@ -493,14 +549,27 @@ extern "C" int blx_analyze_device(blx_engine *e, int fmt, const void *d_pcm, con
                                   const int *channels, const uint64_t *duration_s, int n_songs, unsigned what,
                                   blx_result *d_out, void *stream) {
     if (!d_out) return fail(BLX_ERR_ARG, "null d_out");
-    return analyze_device_impl(e, fmt, d_pcm, offsets, lengths, channels, duration_s, n_songs, what, d_out, nullptr, stream);
+    return analyze_device_impl(e, fmt, d_pcm, offsets, lengths, channels, duration_s, n_songs, what, d_out, nullptr, stream, false);
+}
+
+extern "C" int blx_analyze_device_async(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets,
+                                        const int64_t *lengths, const int *channels, const uint64_t *duration_s, int n_songs,
+                                        unsigned what, blx_result *d_out, void *stream) {
+    if (!d_out) return fail(BLX_ERR_ARG, "null d_out");
+    return analyze_device_impl(e, fmt, d_pcm, offsets, lengths, channels, duration_s, n_songs, what, d_out, nullptr, stream, true);
+}
+
+extern "C" int blx_join(blx_engine *e, void *stream) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    return join_stream(e, stream ? static_cast<cudaStream_t>(stream) : e->compute);
 }
 
 extern "C" int blx_spectral_device(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets, const int64_t *lengths,
                                    const int *channels, int n_songs, float *d_frequency, void *stream) {
     if (!d_frequency) return fail(BLX_ERR_ARG, "null d_frequency");
     return analyze_device_impl(e, fmt, d_pcm, offsets, lengths, channels, nullptr, n_songs, BLX_DO_FREQUENCY, nullptr,
-                               d_frequency, stream);
+                               d_frequency, stream, false);
 }
 
 // ---------------------------------------------------------------- host-buffer entry points
@@ -573,11 +642,11 @@ static int analyze_host_impl(blx_engine *e, int fmt, const T *const *pcm, const 
         CK(cudaEventRecord(s.copied, e->copy));
         CK(cudaStreamWaitEvent(e->compute, s.copied, 0));
         mark(e->compute);
-        rc = run_chunk(e, s, plan, s.pcm.p, n, what, static_cast<blx_result *>(s.results.p), nullptr, e->compute, true);
+        rc = run_chunk(e, s, plan, s.pcm.p, n, what, static_cast<blx_result *>(s.results.p), nullptr, e->compute, e->tail, true);
         if (rc) return rc;
-        mark(e->compute);
-        CK(cudaMemcpyAsync(s.h_results, s.results.p, (size_t)n * sizeof(blx_result), cudaMemcpyDeviceToHost, e->compute));
-        CK(cudaEventRecord(s.done, e->compute));
+        mark(e->tail);
+        CK(cudaMemcpyAsync(s.h_results, s.results.p, (size_t)n * sizeof(blx_result), cudaMemcpyDeviceToHost, e->tail));
+        CK(cudaEventRecord(s.done, e->tail));
         s.busy = true;
         pending[si] = i0;
         pending_n[si] = n;

@@ -96,15 +96,21 @@ class Engine:
 
     # ------------------------------------------------------------------ device resident
     def analyze_device(self, fmt, d_pcm, offsets, lengths, d_out, durations=None, channels=None, what=DO_ALL,
-                       stream=None):
+                       stream=None, wait=True):
+        """wait=False: blx_analyze_device_async - `stream` is not made to wait for the results; call join(stream)
+        after the last batch of the job."""
         n = len(offsets)
         offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
         lens = (ctypes.c_int64 * n)(*[int(x) for x in lengths])
         durs = (ctypes.c_uint64 * n)(*[int(d) for d in durations]) if durations is not None else None
         chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
-        self._ck(self._lib.blx_analyze_device(self._h, fmt, ctypes.c_void_p(int(d_pcm)), offs, lens, chs, durs, n,
-                                              what, ctypes.c_void_p(int(d_out)),
-                                              ctypes.c_void_p(int(stream)) if stream else None))
+        f = self._lib.blx_analyze_device if wait else self._lib.blx_analyze_device_async
+        self._ck(f(self._h, fmt, ctypes.c_void_p(int(d_pcm)), offs, lens, chs, durs, n, what, ctypes.c_void_p(int(d_out)),
+                   ctypes.c_void_p(int(stream)) if stream else None))
+
+    def join(self, stream=None):
+        """Makes `stream` wait for every analysis enqueued so far (after analyze_device(..., wait=False))."""
+        self._ck(self._lib.blx_join(self._h, ctypes.c_void_p(int(stream)) if stream else None))
 
     def spectral_device(self, fmt, d_pcm, offsets, lengths, d_frequency, channels=None, stream=None):
         n = len(offsets)
@@ -196,6 +202,10 @@ class Engine:
         self._ck(self._lib.blx_envelope_tail(self._h, E.ctypes.data_as(L.c_f64p), len(E), int(n_samples), int(duration),
                                              ctypes.byref(beat), ctypes.byref(tempo), ctypes.byref(attack)))
         return dict(beat=beat.value, tempo=tempo.value, attack=attack.value)
+
+    def configure_sub_batch(self, songs):
+        """Songs per kernel sequence of the device-resident entry points (results do not depend on it)."""
+        self._ck(self._lib.blx_configure_sub_batch(self._h, int(songs)))
 
     def debug_flags(self, flags):
         """Test hooks (include/blx.h BLX_DEBUG_*); results must not depend on them."""

@@ -74,6 +74,10 @@ const char *blx_last_error(void);
  * two device staging buffers used by the host-buffer entry points (default 1 GiB). */
 int blx_configure(blx_engine *e, size_t chunk_bytes);
 
+/* Songs per kernel sequence of the device-resident entry points (default 512, or $BLX_SUB_BATCH at blx_init).
+ * Results do not depend on it. */
+int blx_configure_sub_batch(blx_engine *e, int songs);
+
 /* Test hooks (results must not depend on them). BLX_DEBUG_SLOW_CHAIN: the envelope kernel takes
  * its fallback path (binade-by-binade scan) for the float accumulation of every hop. */
 #define BLX_DEBUG_SLOW_CHAIN 1u
@@ -97,10 +101,20 @@ int blx_analyze_batch_f32(blx_engine *e, const float *const *pcm, const int64_t 
  * are HOST arrays in elements; channels (S16 only, NULL => 2) and duration_s (S16 only;
  * F32 derives it) are HOST arrays. d_out: DEVICE array of n_songs blx_result.
  * stream: a cudaStream_t passed as void* (NULL = the engine's own stream). The call
- * only enqueues work; it does not synchronise. */
+ * only enqueues work; it does not synchronise. The kernels run on the engine's own streams (sub-batches of 512
+ * songs; the sequential tail of one under the envelope kernel of the next), fenced against `stream` on both
+ * sides: work enqueued on `stream` before the call is seen, work enqueued after it sees the results. */
 int blx_analyze_device(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets,
                        const int64_t *lengths, const int *channels, const uint64_t *duration_s, int n_songs,
                        unsigned what, blx_result *d_out, void *stream);
+
+/* Same, for a job of several batches: the call returns without making `stream` wait for the results, so that the
+ * latency-bound tail of this batch runs under the next batch's kernels. Inputs and d_out must stay untouched
+ * until blx_join(e, stream), which makes `stream` wait for everything enqueued so far. */
+int blx_analyze_device_async(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets,
+                             const int64_t *lengths, const int *channels, const uint64_t *duration_s, int n_songs,
+                             unsigned what, blx_result *d_out, void *stream);
+int blx_join(blx_engine *e, void *stream);
 
 /* The fused window + rFFT-512 + per-bin power + band-ratio kernel ALONE
  * (BASELINE.json configs[1]); writes only `frequency` per song to d_frequency

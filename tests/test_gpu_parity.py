@@ -521,3 +521,43 @@ def test_bl_distance_file_two_different_files(engine, oracle, tmp_path):
     assert rel(d, oracle.distance(o1, o2)) <= 1e-4
     assert s2.nSamples == len(pcm) and s2.duration == 9
     L.bl_free_song(ctypes.byref(s1)); L.bl_free_song(ctypes.byref(s2))
+
+
+def test_sub_batches_and_pipelined_calls_are_byte_identical(engine):
+    """The device-resident path cuts a batch into sub-batches (tail of one under the envelope kernel of the next, two
+    streams) and a job may enqueue several batches before joining: records are byte-identical to one sub-batch per call."""
+    import torch
+    songs = [song_f32(800 + i, s) for i, s in enumerate([3.0, 7.5, 2.2, 12.0, 4.0, 2.0, 9.1, 5.5, 3.3, 6.0, 2.7])]
+    offs, total = [], 0
+    for x in songs:
+        offs.append(total)
+        total += (len(x) + 63) // 64 * 64 + 64
+    buf = torch.zeros(total, dtype=torch.float32, device="cuda")
+    for o, x in zip(offs, songs):
+        buf[o:o + len(x)] = torch.from_numpy(x).cuda()
+    lens = [len(x) for x in songs]
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        ref = torch.zeros(len(songs) * 8, dtype=torch.int32, device="cuda")
+        engine.analyze_device(bliss_b200.FMT_F32, buf.data_ptr(), offs, lens, ref.data_ptr(), stream=st.cuda_stream)
+        st.synchronize()
+        want = ref.cpu().numpy().tobytes()
+        small = bliss_b200.Engine(0)
+        try:
+            small.configure_sub_batch(3)  # 3 + 3 + 3 + 2 songs: all four slots in rotation
+            out = torch.zeros_like(ref)
+            small.analyze_device(bliss_b200.FMT_F32, buf.data_ptr(), offs, lens, out.data_ptr(), stream=st.cuda_stream)
+            st.synchronize()
+            assert out.cpu().numpy().tobytes() == want
+            # three pipelined calls (5 + 4 + 2 songs) into one result array, one join
+            out2 = torch.zeros_like(ref)
+            for a, b in ((0, 5), (5, 9), (9, 11)):
+                small.analyze_device(bliss_b200.FMT_F32, buf.data_ptr(), offs[a:b], lens[a:b], out2.data_ptr() + 32 * a,
+                                     stream=st.cuda_stream, wait=False)
+            small.join(st.cuda_stream)
+            # work enqueued on the caller's stream after the join sees the results
+            copy = out2.clone()
+            st.synchronize()
+            assert copy.cpu().numpy().tobytes() == want
+        finally:
+            small.close()
