@@ -16,6 +16,7 @@
 
 #include "blx_common.cuh"
 #include "kernels.h"
+#include "../../include/blx_resample.h"
 
 using namespace blx;
 
@@ -761,6 +762,55 @@ extern "C" int blx_frontend_f32(blx_engine *e, const float *pcm, int64_t n_in, i
     CK(launch_frontend(static_cast<const float *>(e->scratch_a.p), n_in, static_cast<short *>(e->scratch_b.p), e->compute));
     CK(cudaMemcpyAsync(out, e->scratch_b.p, (size_t)(n_in / 2) * 4, cudaMemcpyDeviceToHost, e->compute));
     CK(cudaStreamSynchronize(e->compute));
+    return BLX_OK;
+}
+
+extern "C" int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int kind, int bits, int channels, int64_t n_frames,
+                                   int in_rate, int16_t *out, int64_t out_capacity_frames, int64_t *n_out_frames) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!samples || !n_out_frames || n_frames <= 0 || (channels != 1 && channels != 2) || kind < 0 || kind > 3 || bits < 1 ||
+        bits > 32 || (kind == BLX_RS_KIND_S16 && bits > 16) || (kind == BLX_RS_KIND_U8 && bits != 8))
+        return fail(BLX_ERR_ARG, "bad resampler arguments");
+    ResampleParams p;
+    memset(&p, 0, sizeof(p));
+    p.kind = kind; p.bits = bits; p.channels = channels; p.n_in = n_frames;
+    std::vector<float> bank_f;
+    std::vector<int16_t> bank_i;
+    if (in_rate == BLX_RS_OUT_RATE) {
+        p.n_out = n_frames;
+    } else {
+        blx_rs_plan plan;
+        if (blx_rs_plan_make(in_rate, BLX_RS_OUT_RATE, &plan))
+            return fail(BLX_ERR_ARG, "sample rate %d Hz needs more than %d filter phases", in_rate, BLX_RS_MAX_PHASES);
+        p.L = plan.L; p.P = plan.P; p.q = plan.q; p.center = plan.center;
+        p.mono_gain_last = BLX_RS_MONO_GAIN_LAST(in_rate) ? 1 : 0;
+        p.n_out = blx_rs_out_frames(&plan, n_frames, nullptr);
+        if (kind == BLX_RS_KIND_U8) { bank_i.resize((size_t)plan.P * plan.L); blx_rs_build_s16(&plan, bank_i.data()); }
+        else { bank_f.resize((size_t)plan.P * plan.L); blx_rs_build_f32(&plan, bank_f.data()); }
+    }
+    *n_out_frames = p.n_out;
+    if (!out) return BLX_OK; // size query
+    if (out_capacity_frames < p.n_out) return fail(BLX_ERR_ARG, "output buffer too small");
+    if (p.n_out == 0) return BLX_OK;
+    const size_t in_bytes = (size_t)n_frames * channels * 4, out_bytes = (size_t)p.n_out * 2 * 2;
+    const size_t bank_bytes = bank_f.size() * 4 + bank_i.size() * 2;
+    CK(e->scratch_a.reserve(in_bytes));
+    CK(e->scratch_b.reserve(out_bytes + ((bank_bytes + 255) & ~(size_t)255) + 256));
+    cudaStream_t st = e->compute;
+    unsigned char *d_bank = static_cast<unsigned char *>(e->scratch_b.p) + ((out_bytes + 255) & ~(size_t)255);
+    CK(cudaMemcpyAsync(e->scratch_a.p, samples, in_bytes, cudaMemcpyHostToDevice, st));
+    if (bank_bytes)
+        CK(cudaMemcpyAsync(d_bank, bank_f.empty() ? (const void *)bank_i.data() : (const void *)bank_f.data(), bank_bytes,
+                           cudaMemcpyHostToDevice, st));
+    p.in = static_cast<const int *>(e->scratch_a.p);
+    p.out = static_cast<short *>(e->scratch_b.p);
+    p.bank_f32 = reinterpret_cast<const float *>(d_bank);
+    p.bank_s16 = reinterpret_cast<const short *>(d_bank);
+    e->launches++;
+    CK(launch_resample(p, st));
+    CK(cudaMemcpyAsync(out, e->scratch_b.p, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return BLX_OK;
 }
 

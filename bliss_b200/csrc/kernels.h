@@ -65,6 +65,18 @@ int distance_nearest_splits(int n, int n_rows, bool with_sum);
 cudaError_t launch_distance_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_dist,
                                     double *d_sum, unsigned long long *d_packed, int splits, cudaStream_t st);
 cudaError_t launch_rect_filter(double *d_out, const double *d_in, int n, int width, cudaStream_t st);
+// decode-stage resampler (include/blx_resample.h): in = the reader's int32 samples (interleaved), out = int16 stereo
+struct ResampleParams {
+    const int *in;
+    short *out;
+    const float *bank_f32;  // [P][L] (float-internal kinds)
+    const short *bank_s16;  // [P][L] (BLX_RS_KIND_U8)
+    long long n_in, n_out;  // frames
+    int kind, bits, channels;
+    int L, P, q, center;    // P == 0: same rate, format conversion only
+    int mono_gain_last;     // BLX_RS_MONO_GAIN_LAST(in_rate)
+};
+cudaError_t launch_resample(const ResampleParams &p, cudaStream_t st);
 cudaError_t launch_dfma_peak(double *d_scratch, int blocks, int threads, int iters, cudaStream_t st);
 cudaError_t launch_frontend(const float *d_in, long long n_in, short *d_out, cudaStream_t st);
 

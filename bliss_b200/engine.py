@@ -162,6 +162,21 @@ class Engine:
         self._ck(self._lib.blx_frontend_f32(self._h, x.ctypes.data_as(L.c_f32p), len(x), out.ctypes.data_as(L.c_i16p)))
         return out
 
+    RS_S16, RS_S32, RS_F32, RS_U8 = 0, 1, 2, 3
+
+    def resample_to_s16(self, samples, kind, bits, channels, in_rate):
+        """Decode-stage resampler (include/blx_resample.h): the reader's int32 samples -> int16 / 22 050 Hz / stereo."""
+        a = np.ascontiguousarray(samples, dtype=np.int32)
+        n = len(a) // channels
+        p = a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        cnt = ctypes.c_int64(0)
+        self._ck(self._lib.blx_resample_to_s16(self._h, p, kind, bits, channels, n, in_rate, None, 0, ctypes.byref(cnt)))
+        out = np.zeros(2 * cnt.value, dtype=np.int16)
+        if cnt.value:
+            self._ck(self._lib.blx_resample_to_s16(self._h, p, kind, bits, channels, n, in_rate, out.ctypes.data_as(L.c_i16p),
+                                                   cnt.value, ctypes.byref(cnt)))
+        return out
+
     def envelope_energy(self, pcm):
         a = np.ascontiguousarray(pcm, dtype=np.int16)
         nb = 2 * (len(a) // 512)

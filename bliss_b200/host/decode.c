@@ -5,14 +5,15 @@
  *
  * Containers: FLAC and RIFF/WAVE via flac_reader.c (the reference uses FFmpeg, absent here).
  * Input that is already int16 / 22 050 Hz is passed through bit for bit, as in the reference
- * (reference src/decode.c:317-318: no resampler is set up). Other rates / sample formats need a
- * resampler; FFmpeg's libswresample is third-party and cannot be matched bit for bit, so they are
- * converted by the engine's own front-end where it applies (44.1 kHz, any bit depth -> mono mix ->
- * blx_frontend.h on the GPU) and rejected otherwise.
+ * (reference src/decode.c:317-318: no resampler is set up). Every other rate / sample format goes
+ * through the resampler of include/blx_resample.h on the GPU (blx_resample_to_s16), a restatement of
+ * libswresample's default polyphase filter that reproduces the reference's md5 pins of its 48 kHz
+ * fixtures (reference tests/test_decode.c:35-36,55-56): stereo stays stereo, mono is up-mixed at -3 dB.
  */
 #include "../../include/bliss.h"
 #include "engine_singleton.h"
 #include "flac_reader.h"
+#include "../../include/blx_resample.h"
 
 static char *dup_or(const char *s, const char *fallback) {
     const char *src = s ? s : fallback;
@@ -44,56 +45,48 @@ int bl_audio_decode(char const *const filename, struct bl_song *const song) {
     song->resampled = 0;
 
     int rc = BL_UNEXPECTED;
-    if (f.sample_rate == 22050 && f.bits_per_sample == 16 && !f.is_float && (f.channels == 1 || f.channels == 2)) {
+    /* what FFmpeg's decoder would hand over: FLAC <= 16 bit and 16-bit PCM as int16 (left-justified), 17..32 bit as
+     * int32, float PCM as float, 8-bit PCM as unsigned bytes */
+    const int is_u8 = f.container == 1 && !f.is_float && f.bits_per_sample == 8;
+    const int is_s16 = !f.is_float && !is_u8 && f.bits_per_sample <= 16;
+    if (f.sample_rate == BLX_RS_OUT_RATE && is_s16 && (f.channels == 1 || f.channels == 2)) {
         /* native format: copied through untouched (a mono file keeps its mono sample count while
          * channels reads 2, exactly as reference src/decode.c:187-193 leaves it) */
         const size_t n = f.n_frames * (size_t)f.channels;
+        const int shift = 16 - f.bits_per_sample;
         int16_t *pcm = (int16_t *)malloc(n * sizeof(int16_t));
         if (pcm) {
-            for (size_t i = 0; i < n; ++i) pcm[i] = (int16_t)f.samples[i];
+            for (size_t i = 0; i < n; ++i) pcm[i] = (int16_t)((uint32_t)f.samples[i] << shift);
             song->sample_array = (int8_t *)pcm;
             song->nSamples = (int)n;
             rc = BL_OK;
         }
-    } else if (f.sample_rate == 44100 && f.channels >= 1) {
-        /* 44.1 kHz: mono mix on the host (I/O stage), 2:1 front-end on the GPU */
-        const size_t n = f.n_frames;
-        float *mono = (float *)malloc(n * sizeof(float));
-        int16_t *pcm = (int16_t *)malloc((n / 2) * 2 * sizeof(int16_t) + 4);
-        if (mono && pcm && n >= 2) {
-            const float scale = f.is_float ? 1.0f : 1.0f / (float)(1u << (f.bits_per_sample - 1));
-            for (size_t i = 0; i < n; ++i) {
-                float acc = 0.0f;
-                for (int c = 0; c < f.channels; ++c) {
-                    const int32_t raw = f.samples[i * (size_t)f.channels + (size_t)c];
-                    float v;
-                    if (f.is_float) memcpy(&v, &raw, 4);
-                    else v = (float)raw * scale;
-                    acc += v;
-                }
-                mono[i] = acc / (float)f.channels;
+    } else if (f.channels == 1 || f.channels == 2) {
+        /* everything else goes through the resampler (reference src/decode.c:313-345: libswresample to
+         * int16 / 22 050 Hz / stereo; here include/blx_resample.h on the GPU) */
+        const int kind = f.is_float ? BLX_RS_KIND_F32 : is_u8 ? BLX_RS_KIND_U8 : is_s16 ? BLX_RS_KIND_S16 : BLX_RS_KIND_S32;
+        blx_engine *e = bl_engine_acquire();
+        if (e) {
+            int64_t n_out = 0;
+            int brc = blx_resample_to_s16(e, f.samples, kind, f.bits_per_sample, f.channels, (int64_t)f.n_frames, f.sample_rate,
+                                          NULL, 0, &n_out);
+            int16_t *pcm = NULL;
+            if (brc == BLX_OK && n_out > 0 && n_out < ((int64_t)1 << 30)) pcm = (int16_t *)malloc((size_t)n_out * 2 * sizeof(int16_t));
+            if (pcm && blx_resample_to_s16(e, f.samples, kind, f.bits_per_sample, f.channels, (int64_t)f.n_frames, f.sample_rate,
+                                           pcm, n_out, &n_out) == BLX_OK) {
+                song->sample_array = (int8_t *)pcm;
+                song->nSamples = (int)(2 * n_out);
+                song->resampled = 1;
+                rc = BL_OK;
+            } else {
+                free(pcm);
+                if (brc != BLX_OK || n_out > 0) fprintf(stderr, "bliss: resampling failed: %s\n", blx_last_error());
             }
-            blx_engine *e = bl_engine_acquire();
-            if (e) {
-                if (blx_frontend_f32(e, mono, (int64_t)n, pcm) == BLX_OK) {
-                    song->sample_array = (int8_t *)pcm;
-                    song->nSamples = (int)((n / 2) * 2);
-                    song->resampled = 1;
-                    pcm = NULL;
-                    rc = BL_OK;
-                } else {
-                    fprintf(stderr, "bliss: front-end failed: %s\n", blx_last_error());
-                }
-                bl_engine_release();
-            }
+            bl_engine_release();
         }
-        free(mono);
-        free(pcm);
     } else {
-        fprintf(stderr,
-                "Couldn't decode %s: %d Hz / %d bit needs a resampler this build does not carry "
-                "(supported: 22050 Hz s16 passthrough, 44100 Hz via the GPU front-end)\n",
-                filename, f.sample_rate, f.bits_per_sample);
+        fprintf(stderr, "Couldn't decode %s: %d channels need a down-mix matrix this build does not carry (mono and stereo only)\n",
+                filename, f.channels);
     }
     blx_pcm_file_free(&f);
     if (rc != BL_OK) {

@@ -222,6 +222,7 @@ static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
     }
     if (!have_info || f->channels < 1 || f->channels > 8) return -1;
     f->is_float = 0;
+    f->container = 0;
 
     size_t cap = total ? (size_t)total : (size_t)1 << 20;
     int32_t *pcm = (int32_t *)malloc(cap * (size_t)f->channels * sizeof(int32_t));
@@ -325,6 +326,7 @@ static int decode_wav(const uint8_t *d, size_t n, blx_pcm_file *f) {
             size_t total = len / (size_t)bytes;
             size_t nframes = total / (size_t)f->channels;
             f->is_float = (fmt_tag == 3);
+            f->container = 1;
             if (f->is_float && bytes != 4) return -1;
             int32_t *pcm = (int32_t *)malloc((total ? total : 1) * sizeof(int32_t));
             if (!pcm) return -1;

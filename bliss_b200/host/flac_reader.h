@@ -11,6 +11,7 @@ typedef struct blx_pcm_file {
     int sample_rate;
     int bits_per_sample;
     int is_float;
+    int container;         /* 0 FLAC, 1 RIFF/WAVE */
     uint64_t file_bytes;
     uint8_t md5[16];       /* FLAC STREAMINFO md5 of the unencoded audio (zero for WAV) */
     char *artist, *title, *album, *tracknumber, *genre; /* NULL when absent */

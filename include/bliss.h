@@ -7,6 +7,11 @@
  * and link unchanged against this library's libbliss.so. Struct ABI (LP64):
  * sizeof(struct bl_song) == 120, sizeof(struct force_vector_s) == 16.
  *
+ * Like the reference header this one carries no extern "C" block and no code outside declarations, so the
+ * text filter of reference python/build_bliss.py:35-38 (drop every line that starts with '#', hand the rest to
+ * cffi's cdef) works on it unchanged (tools/build_ref_cffi.py, tests/test_ref_callers.py); C++ callers wrap the
+ * include themselves, as they have to with the reference.
+ *
  * Differences from the reference header, none of which change the ABI:
  *  - the FFmpeg headers (reference include/bliss.h:5-6) are optional: they are only
  *    needed there for a version shim; the libc headers they used to pull in are
@@ -17,6 +22,7 @@
 #ifndef BL_BLISS_H_
 #define BL_BLISS_H_
 
+#include <inttypes.h> /* PRId64: reference examples/analyze.c:40 gets it through the FFmpeg headers */
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -28,10 +34,6 @@
 #include <libavformat/avformat.h>
 #include <libavutil/md5.h>
 #endif
-#endif
-
-#ifdef __cplusplus
-extern "C" {
 #endif
 
 #ifndef M_PI
@@ -136,7 +138,4 @@ int bl_variance(int16_t *sample_array, int nSamples, int mean);
 void bl_rectangular_filter(double *sample_array_out, double *sample_array_in, int nSamples,
                            int smooth_width);
 
-#ifdef __cplusplus
-}
-#endif
 #endif /* BL_BLISS_H_ */

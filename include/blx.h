@@ -158,6 +158,13 @@ int blx_rectangular_filter(blx_engine *e, double *out, const double *in, int n, 
  * (2 * (n_in / 2) values). */
 int blx_frontend_f32(blx_engine *e, const float *pcm, int64_t n_in, int16_t *out);
 
+/* Decode-stage resampler (include/blx_resample.h), replacing the libswresample calls of reference
+ * src/decode.c:313-345,388-392: the reader's int32 samples (interleaved, `kind` / `bits` as in blx_resample.h,
+ * 1 or 2 channels, in_rate Hz) to int16 / 22 050 Hz / stereo, host to host. out == NULL only returns the
+ * number of output frames. */
+int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int kind, int bits, int channels, int64_t n_frames,
+                        int in_rate, int16_t *out, int64_t out_capacity_frames, int64_t *n_out_frames);
+
 /* Envelope intermediates for kernel-level parity tests: hop energies E[m]
  * (reference src/tempo_atk_sort.c:150), 2 * (n_samples / 512) doubles, host. */
 int blx_envelope_energy_s16(blx_engine *e, const int16_t *pcm, int n_samples, double *energy);

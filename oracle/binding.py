@@ -102,6 +102,9 @@ class Oracle:
         L.orc_distance_matrix.argtypes = [_f32p, ctypes.c_int, _f32p]
         L.orc_frontend_f32.restype = ctypes.c_int
         L.orc_frontend_f32.argtypes = [_f32p, ctypes.c_long, _i16p]
+        L.orc_resample_to_s16.restype = ctypes.c_longlong
+        L.orc_resample_to_s16.argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_longlong, ctypes.c_int, _i16p]
 
     # -- analysers ---------------------------------------------------
     def frequency(self, pcm, channels=2):
@@ -190,6 +193,23 @@ class Oracle:
         x = np.ascontiguousarray(x, dtype=np.float32)
         out = np.zeros(2 * (len(x) // 2), dtype=np.int16)
         self.lib.orc_frontend_f32(x.ctypes.data_as(_f32p), len(x), out.ctypes.data_as(_i16p))
+        return out
+
+
+    # -- decode-stage resampler (include/blx_resample.h) -----------------
+    RS_S16, RS_S32, RS_F32, RS_U8 = 0, 1, 2, 3
+
+    def resample_to_s16(self, samples, kind, bits, channels, in_rate):
+        """samples: the reader's int32 array (interleaved; float32 bits for RS_F32). Returns int16 stereo interleaved
+        at 22 050 Hz as libswresample with default options produces it."""
+        a = np.ascontiguousarray(samples, dtype=np.int32)
+        n = len(a) // channels
+        p = a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        cnt = self.lib.orc_resample_to_s16(p, kind, bits, channels, n, in_rate, None)
+        if cnt < 0:
+            raise ValueError("unsupported resampling request")
+        out = np.zeros(2 * cnt, dtype=np.int16)
+        self.lib.orc_resample_to_s16(p, kind, bits, channels, n, in_rate, out.ctypes.data_as(_i16p))
         return out
 
 

@@ -56,33 +56,36 @@ def test_decode_error_paths(tmp_path, capfd):
     L.bl_free_song(ctypes.byref(s))  # a failed decode can still be freed (reference examples/analyze.c:15-17,50-52)
     (tmp_path / "junk.wav").write_bytes(b"not audio at all" * 10)
     assert decode(tmp_path / "junk.wav")[2] == -2
-    write_wav(tmp_path / "r48.wav", song_s16(6, 1.0), 48000, 2, 1, 16)  # needs a resampler this build does not carry
-    assert decode(tmp_path / "r48.wav")[2] == -2
-    assert "resampler" in capfd.readouterr().err
+    six = np.zeros(6 * 500, dtype=np.int16)
+    write_wav(tmp_path / "six.wav", six, 22050, 6, 1, 16)  # 5.1: no down-mix matrix in this build
+    assert decode(tmp_path / "six.wav")[2] == -2
+    assert "down-mix" in capfd.readouterr().err
     assert L.bl_analyze(str(tmp_path / "missing.flac").encode(), ctypes.byref(bliss_b200.BlSong())) == -2
 
 
 @pytest.mark.gpu
-def test_wav_44k_routes_through_the_gpu_frontend(tmp_path, engine, oracle):
-    x = song_f32(7, 4.0)
-    xs = np.stack([x * 0.9, x * 0.5], axis=1)  # stereo: the host mixes to mono before the 2:1 front-end
-    write_wav(tmp_path / "f32m.wav", x, 44100, 1, 3, 32)
-    write_wav(tmp_path / "s16s.wav", np.round(xs * 32767).astype(np.int16), 44100, 2, 1, 16)
-    write_wav(tmp_path / "s24m.wav", np.round(x * 8388607).astype(np.int32), 44100, 1, 1, 24)
+def test_files_at_other_rates_and_formats_go_through_the_resampler(tmp_path, oracle):
+    """bl_audio_decode on WAV files that are not int16 / 22 050 Hz: the GPU resampler (include/blx_resample.h) gives what the
+    oracle restatement of libswresample gives, bit for bit - stereo stays stereo, mono is up-mixed, every bit depth."""
+    x = song_f32(7, 3.0)
+    xs = np.stack([x * 0.9, np.roll(x, 17) * 0.5], axis=1)
     L = bliss_b200.load()
-    # float32 mono: exactly the engine's float path
-    s = bliss_b200.BlSong()
-    assert L.bl_analyze(str(tmp_path / "f32m.wav").encode(), ctypes.byref(s)) in (0, 1, 2)
-    ref = engine.analyze_f32([x])[0]
-    assert s.resampled == 1 and s.nSamples == 2 * (len(x) // 2) and s.duration == 4
-    assert np.array_equal(pcm_of(s), oracle.frontend_f32(x))
-    assert (s.force_vector.tempo, s.force_vector.amplitude, s.force_vector.frequency, s.force_vector.attack, s.force) == (
-        ref["tempo"], ref["amplitude"], ref["frequency"], ref["attack"], ref["force"])
-    L.bl_free_song(ctypes.byref(s))
-    # int16 stereo and packed int24 mono: scaled to [-1, 1), mixed, then the same front-end
-    for name, mono in (("s16s.wav", ((np.round(xs * 32767).astype(np.int16).astype(np.float32) / 32768.0).sum(axis=1) / 2).astype(np.float32)),
-                       ("s24m.wav", (np.round(x * 8388607).astype(np.int32).astype(np.float32) / 8388608.0).astype(np.float32))):
-        s = bliss_b200.BlSong()
-        assert L.bl_audio_decode(str(tmp_path / name).encode(), ctypes.byref(s)) == 0, name
-        assert np.array_equal(pcm_of(s), oracle.frontend_f32(mono)), name
+    cases = [("f32m_44.wav", x, 44100, 1, 3, 32, oracle.RS_F32, x.view(np.int32)),
+             ("s16s_44.wav", np.round(xs * 32767).astype(np.int16), 44100, 2, 1, 16, oracle.RS_S16, None),
+             ("s24m_48.wav", np.round(x * 8388607).astype(np.int32), 48000, 1, 1, 24, oracle.RS_S32, None),
+             ("s16s_48.wav", np.round(xs * 32767).astype(np.int16), 48000, 2, 1, 16, oracle.RS_S16, None),
+             ("s32s_96.wav", np.round(xs * 2147483000).astype(np.int32), 96000, 2, 1, 32, oracle.RS_S32, None),
+             ("u8s_8.wav", (np.round(xs[:20000] * 127) + 128).astype(np.uint8), 8000, 2, 1, 8, oracle.RS_U8, None),
+             ("s24s_22.wav", np.round(xs * 8388607).astype(np.int32), 22050, 2, 1, 24, oracle.RS_S32, None)]
+    for name, data, rate, ch, tag, bits, kind, raw in cases:
+        write_wav(tmp_path / name, data, rate, ch, tag, bits)
+        _, s, rc = decode(tmp_path / name)
+        assert rc == 0, name
+        if raw is None:
+            raw = np.asarray(data).astype(np.int32) - (128 if bits == 8 else 0)
+        want = oracle.resample_to_s16(raw.reshape(-1), kind, bits, ch, rate)
+        got = pcm_of(s)
+        assert s.resampled == 1 and s.channels == 2 and s.sample_rate == 22050 and s.nSamples == len(want), name
+        assert s.duration == len(np.asarray(data).reshape(-1, ch)) // rate, name
+        assert np.array_equal(got, want), (name, int(np.abs(got.astype(int) - want).max()))
         L.bl_free_song(ctypes.byref(s))

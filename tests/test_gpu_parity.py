@@ -56,14 +56,47 @@ def test_bl_analyze_golden_fixture(oracle):
     assert rel(got["frequency"], ref["frequency"]) <= 1e-5
 
 
-def test_second_golden_fixture_s32(engine):
-    """reference tests/test_analyze.c:59-78: audio/song_s32.flac after the reference's decode + resample
-    (fixture tests/golden/song_s32_pcm.npz, md5-pinned): force vector within the reference's own 1e-5, beat 61."""
-    from test_oracle import GOLDEN_S32, load_s32_pcm
-    res = engine.analyze_s16([load_s32_pcm()], [GOLDEN_S32["duration"]])[0]
-    assert res["status"] == 0 and int(res["beat"]) == GOLDEN_S32["beat"] and int(res["calm_or_loud"]) == 1
-    for k in ("force", "tempo", "amplitude", "frequency", "attack"):
-        assert abs(float(res[k]) - GOLDEN_S32[k]) <= 1e-5, (k, float(res[k]), GOLDEN_S32[k])
+def test_second_golden_fixture_s32(oracle):
+    """reference tests/test_analyze.c:59-90 verbatim: bl_analyze on audio/song_s32.flac (48 kHz / 24 bit) - decoded by the
+    host FLAC reader, resampled on the GPU (include/blx_resample.h) - gives the reference's force vector to its own 1e-5,
+    its field values, and the md5 of the resampled PCM that reference tests/test_decode.c:35-36 pins; same for the mono file."""
+    import hashlib
+    from test_oracle import GOLDEN_S32, GOLDEN_S32_MD5, GOLDEN_S32_MONO_MD5
+    L = bliss_b200.load()
+    for name, md5 in (("song_s32.flac", GOLDEN_S32_MD5), ("song_s32_mono.flac", GOLDEN_S32_MONO_MD5)):
+        s = bliss_b200.BlSong()
+        rc = L.bl_analyze(os.path.join(GOLDEN_DIR, name).encode(), ctypes.byref(s))
+        assert rc == 1, name  # BL_CALM
+        pcm = np.ctypeslib.as_array(ctypes.cast(s.sample_array, ctypes.POINTER(ctypes.c_int16)), (s.nSamples,)).copy()
+        assert hashlib.md5(pcm.tobytes()).hexdigest() == md5, name
+        assert (s.nSamples, s.channels, s.sample_rate, s.nb_bytes_per_sample, s.duration, s.resampled) == (488140, 2, 22050, 2, 11, 1)
+        assert (s.artist, s.title, s.album, s.tracknumber, s.genre) == (b"David TMX", b"Renaissance", b"Renaissance", b"02", b"Pop")
+        if name == "song_s32.flac":
+            assert s.bitrate == 840742  # reference tests/test_analyze.c:74
+            got = dict(force=s.force, tempo=s.force_vector.tempo, amplitude=s.force_vector.amplitude,
+                       frequency=s.force_vector.frequency, attack=s.force_vector.attack)
+            for k, v in got.items():
+                assert abs(v - GOLDEN_S32[k]) <= 1e-5, (k, v, GOLDEN_S32[k])
+        else:
+            ref = oracle.analyze(pcm, 11)
+            assert int(round((s.force_vector.tempo + 30.4) * 11 / 4)) == ref["beat"] and rel(s.force, ref["force"]) <= REL_TOL
+        L.bl_free_song(ctypes.byref(s))
+
+
+def test_resampler_kernel_matches_oracle(engine, oracle):
+    """blx_resample_to_s16 against the oracle on the libswresample fixtures and on seeded signals: bit-exact."""
+    z = np.load(os.path.join(GOLDEN_DIR, "resample_vectors.npz"))
+    kinds = dict(s16=engine.RS_S16, s32=engine.RS_S32, f32=engine.RS_F32, u8=engine.RS_U8)
+    for key in sorted(k[:-3] for k in z.files if k.endswith("_in")):
+        kind, bits, ch, rate = key.split("_")
+        got = engine.resample_to_s16(z[key + "_in"], kinds[kind], int(bits), int(ch), int(rate))
+        assert np.array_equal(got, z[key + "_out"]), key
+    rng = np.random.default_rng(77)
+    for rate, ch, n in ((48000, 2, 100003), (32000, 1, 50000), (12000, 2, 30000), (192000, 2, 90001), (7350, 1, 9000)):
+        x = (rng.standard_normal(n * ch) * 7000).clip(-32768, 32767).astype(np.int32)
+        assert np.array_equal(engine.resample_to_s16(x, engine.RS_S16, 16, ch, rate), oracle.resample_to_s16(x, oracle.RS_S16, 16, ch, rate)), rate
+    with pytest.raises(bliss_b200.BlxError):
+        engine.resample_to_s16(np.zeros(4000, np.int32), engine.RS_S16, 16, 2, 47999)  # 22050 / 47999: more than 1024 phases
 
 
 # ---------------------------------------------------------------- native int16 input

@@ -16,17 +16,28 @@ GOLDEN_S16 = dict(force=-20.777929, tempo=-8.945454, amplitude=-10.641844, frequ
 # reference tests/test_decode.c:16-17
 GOLDEN_S16_MD5 = "8a1bd824951c0433cc47fec5bf41d0a9"
 # reference tests/test_analyze.c:59-78 (audio/song_s32.flac, 48 kHz / 24 bit, through libswresample) and
-# tests/test_decode.c:35-36; the decoded PCM is the committed fixture made by tools/make_golden_s32.py
+# tests/test_decode.c:35-36,55-56; the fixtures are decoded by the product's FLAC reader and resampled by the
+# oracle restatement of libswresample (oracle/resample.c), md5-pinned
 GOLDEN_S32 = dict(force=-20.821571, tempo=-8.218182, amplitude=-10.641695, frequency=-10.179875,
                   attack=-15.561186, nSamples=488140, duration=11, beat=61)
 GOLDEN_S32_MD5 = "eb9f31a7b9ed022d66ff82b76e7c3c18"
+GOLDEN_S32_MONO_MD5 = "747dbfcd75bebc23ebe2024935aede36"
+_S32_CACHE = {}
 
 
-def load_s32_pcm():
-    pcm = np.load(os.path.join(GOLDEN_DIR, "song_s32_pcm.npz"))["pcm"]
-    assert pcm.dtype == np.int16 and len(pcm) == GOLDEN_S32["nSamples"]
-    assert hashlib.md5(pcm.tobytes()).hexdigest() == GOLDEN_S32_MD5
-    return pcm
+def load_s32_pcm(name="song_s32.flac", md5=GOLDEN_S32_MD5):
+    """The reference's 48 kHz / 24-bit fixture as its decoder hands it to the analysers: int16 / 22 050 Hz / stereo."""
+    if name not in _S32_CACHE:
+        from flac_util import read_pcm_file
+        from oracle.binding import Oracle
+        orc = Oracle()
+        a, n, ch, rate, bps = read_pcm_file(os.path.join(GOLDEN_DIR, name))
+        assert (n, rate, bps) == (531307, 48000, 24)
+        pcm = orc.resample_to_s16(a, orc.RS_S32, bps, ch, rate)
+        assert pcm.dtype == np.int16 and len(pcm) == GOLDEN_S32["nSamples"]
+        assert hashlib.md5(pcm.tobytes()).hexdigest() == md5  # reference tests/test_decode.c:35-36 / :55-56
+        _S32_CACHE[name] = pcm
+    return _S32_CACHE[name]
 
 
 @pytest.fixture(scope="module")
@@ -168,3 +179,36 @@ def test_chain_model_against_sequential_chain(tmp_path):
     stats = dict(zip(last[0::2], last[1::2]))
     assert stats["mismatches"] == "0", out
     assert int(stats["fallback"]) < 120000 * 1e-3, out  # verified fast path on > 99.9 % of the spectra
+
+
+# ---------------------------------------------------------------- decode-stage resampler (include/blx_resample.h)
+def test_resampler_reproduces_reference_md5_pins():
+    """reference tests/test_decode.c:27-65: both 48 kHz fixtures through our FLAC reader and the oracle restatement of
+    libswresample give the reference's md5 (load_s32_pcm asserts it), the mono one up-mixed to L == R."""
+    load_s32_pcm()
+    mono = load_s32_pcm("song_s32_mono.flac", GOLDEN_S32_MONO_MD5)
+    assert np.array_equal(mono[0::2], mono[1::2])
+
+
+def test_resampler_matches_libswresample_vectors(oracle):
+    """tests/golden/resample_vectors.npz (tools/make_golden_resample.py): seeded inputs and what libswresample 6.1.100
+    made of them - every rate / sample format / channel count bit for bit."""
+    z = np.load(os.path.join(GOLDEN_DIR, "resample_vectors.npz"))
+    keys = sorted(k[:-3] for k in z.files if k.endswith("_in"))
+    assert len(keys) >= 20
+    kinds = dict(s16=oracle.RS_S16, s32=oracle.RS_S32, f32=oracle.RS_F32, u8=oracle.RS_U8)
+    for key in keys:
+        kind, bits, ch, rate = key.split("_")
+        got = oracle.resample_to_s16(z[key + "_in"], kinds[kind], int(bits), int(ch), int(rate))
+        assert np.array_equal(got, z[key + "_out"]), key
+
+
+def test_resampler_plan_properties(oracle):
+    """DC gain 1 in every phase, linear phase, and the frame counts libswresample produces."""
+    for rate, frames, want in ((48000, 531307, 244070), (44100, 20001, 10001), (8000, 9999, 27560), (96000, 13844, 3180)):
+        x = np.zeros(frames * 2, dtype=np.int32)
+        assert len(oracle.resample_to_s16(x, oracle.RS_S16, 16, 2, rate)) == 2 * want, rate
+    dc = np.full(2 * 6000, 12345, dtype=np.int32)
+    for rate in (48000, 44100, 32000, 11025):
+        y = oracle.resample_to_s16(dc, oracle.RS_S16, 16, 2, rate)
+        assert np.all(np.abs(y.astype(np.int32) - 12345) <= 1), rate  # mirrored ends: no edge transient either
