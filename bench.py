@@ -476,6 +476,67 @@ def chain_leg(torch, eng, E, dev, stream, rank, world, dist, barrier, max_over_r
             "generation_s_untimed": gen_s}
 
 
+# ------------------------------------------------------------------------------------------ drop-in path
+def bl_analyze_leg(torch, buf, stride, n_in, n_files=8):
+    """songs/s through the reference's own entry point, bl_analyze(filename, &song) of include/bliss.h: file read + decode
+    on the host, analysis on the GPU, per call; from 1 caller thread and from 8 (each call takes an engine out of the
+    library's pool, so concurrent callers overlap on the GPU). Files: the reference's 11-s fixture and 3-minute WAVs in
+    the analysers' native format (int16 / 22 050 Hz / stereo, written from the step's first songs)."""
+    import struct
+    import threading
+
+    import bliss_b200
+    L = bliss_b200.load()
+    out = {}
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        wavs = []
+        n16 = 2 * (n_in // 2)
+        for i in range(n_files):
+            mono = torch.clamp(torch.round(buf[i * stride:i * stride + n_in:2][:n16 // 2] * 32768.0), -32768, 32767).to(torch.int16)
+            pcm = torch.stack([mono, torch.roll(mono, 3)], dim=1).reshape(-1).cpu().numpy()
+            raw = pcm.tobytes()
+            path = os.path.join(d, f"song{i}.wav")
+            with open(path, "wb") as f:
+                f.write(b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " +
+                        struct.pack("<IHHIIHH", 16, 1, 2, 22050, 22050 * 4, 4, 16) + b"data" + struct.pack("<I", len(raw)) + raw)
+            wavs.append(path.encode())
+        fixture = os.path.join(ROOT, "tests", "golden", "song.flac").encode()
+
+        def run(files, threads, reps):
+            recs, lock = {}, threading.Lock()
+
+            def work(tid):
+                for r in range(reps):
+                    for k in range(tid, len(files), threads):
+                        s = bliss_b200.BlSong()
+                        rc = L.bl_analyze(files[k], ctypes.byref(s))
+                        rec = (rc, s.force, s.force_vector.tempo, s.force_vector.amplitude, s.force_vector.frequency, s.force_vector.attack)
+                        L.bl_free_song(ctypes.byref(s))
+                        with lock:
+                            recs.setdefault(k, set()).add(rec)
+            ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+            t0 = time.perf_counter()
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            dt = time.perf_counter() - t0
+            return len(files) * reps / dt, recs
+
+        run(wavs[:2], 1, 1)  # warm-up: engine pool, kernel attributes
+        run(wavs, 8, 1)
+        one, r1 = run(wavs, 1, 2)
+        many, r8 = run(wavs, 8, 4)
+        same = all(len(v) == 1 for v in r1.values()) and all(len(v) == 1 for v in r8.values()) and all(r1[k] == r8[k] for k in r1)
+        fx1, _ = run([fixture] * 8, 1, 2)
+        fx8, _ = run([fixture] * 8, 8, 4)
+        out = {"api": "bl_analyze (include/bliss.h), one file per call: host read + decode, GPU analysis",
+               "wav_3min_songs_per_s_1_thread": one, "wav_3min_songs_per_s_8_threads": many,
+               "fixture_11s_songs_per_s_1_thread": fx1, "fixture_11s_songs_per_s_8_threads": fx8,
+               "results_identical_across_threads": bool(same), "files": n_files}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -807,6 +868,11 @@ def run_ours(args):
         rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)
         parity = {"songs": S, "max_rel_err": float(rel.max()), "tolerance": 1e-4, "ok": bool(rel.max() <= 1e-4)}
 
+    # ---------------- the drop-in entry point, file by file (rank 0)
+    bl_path = None
+    if rank == 0 and not args.no_bl_analyze:
+        bl_path = bl_analyze_leg(torch, buf, stride, n_in)
+
     # ---------------- parity campaign (all ranks) and configs[4] chained
     campaign = None
     if args.parity_songs > 0 and not args.no_cpu:
@@ -827,7 +893,7 @@ def run_ours(args):
             "dtype": "f64 (envelope) + f32 (spectrum) + int64 (statistics)", "data": "synthetic",
             "config": workload_config(args, B, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_kernels": kernels, "spectral_only": spectral, "native_s16": native, "all_pairs": all_pairs, "cpu_baseline": cpu_baseline,
-            "parity": campaign if campaign is not None else parity, "parity_sample": parity, "configs4_chained": chain,
+            "parity": campaign if campaign is not None else parity, "parity_sample": parity, "configs4_chained": chain, "bl_analyze_path": bl_path,
         }
         print(json.dumps(line), flush=True)
     eng.close()
@@ -849,6 +915,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spectral", action="store_true")
     ap.add_argument("--no-distance", action="store_true")
+    ap.add_argument("--no-bl-analyze", action="store_true")
     ap.add_argument("--distance-vectors", type=int, default=1 << 20)
     ap.add_argument("--parity-songs", type=int, default=4096, help="songs of the parity campaign, all ranks together (0 = off)")
     ap.add_argument("--chain-songs", type=int, default=32768,

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/blx.h"
 #include "../../include/blx_frontend.h"
 
@@ -109,16 +111,22 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 
 // ---------------------------------------------------------------- host: once-per-device set-up
-// cudaFuncSetAttribute applies to the current device only; a process may run one engine per GPU.
+// cudaFuncSetAttribute applies to the current device only; a process may run several engines per GPU, from
+// several threads (blx.h). run(f) calls f exactly once per device, under a lock, and every caller returns only
+// after it has completed.
 struct PerDeviceOnce {
+    std::mutex mu;
     bool done[64] = {false};
-    // true if `fn` still has to run for the current device (and marks it as run)
-    bool first_time() {
+    template <typename F> cudaError_t run(F f) {
         int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-        if (done[dev]) return false;
-        done[dev] = true;
-        return true;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64) return f();
+        std::lock_guard<std::mutex> lock(mu);
+        if (done[dev]) return cudaSuccess;
+        e = f();
+        if (e == cudaSuccess) done[dev] = true;
+        return e;
     }
 };
 

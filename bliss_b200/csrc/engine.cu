@@ -37,6 +37,14 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 extern "C" const char *blx_last_error(void) { return g_err; }
+// for the other translation units of the library (multi.cu)
+extern "C" int blx_set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 
 // ---------------------------------------------------------------- grow-only device buffer
 struct DevBuf {

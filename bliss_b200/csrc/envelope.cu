@@ -731,12 +731,12 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
 
 cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, cudaStream_t st) {
     static PerDeviceOnce once;
-    if (once.first_time()) {
+    const cudaError_t e0 = once.run([] {
         cudaError_t e = cudaFuncSetAttribute(envelope_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<true>::bytes);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(envelope_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<false>::bytes);
-        if (e != cudaSuccess) return e;
-    }
+        return cudaFuncSetAttribute(envelope_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<false>::bytes);
+    });
+    if (e0 != cudaSuccess) return e0;
     if (max_hops <= 0) return cudaSuccess;
     if (p.dup) {
         dim3 grid((unsigned)((max_hops + EG<true>::hops_per_cta - 1) / EG<true>::hops_per_cta), (unsigned)n_songs);

@@ -535,10 +535,9 @@ template <int KIND, bool FULL> static cudaError_t launch_one(const Pass1Params &
     using SM = P1Smem<KIND>;
     const int bytes = FULL ? SM::bytes_full : SM::bytes_lite;
     static PerDeviceOnce once;
-    if (once.first_time()) {
-        cudaError_t e = cudaFuncSetAttribute(pass1_kernel<KIND, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return e;
-    }
+    const cudaError_t e0 =
+        once.run([bytes] { return cudaFuncSetAttribute(pass1_kernel<KIND, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+    if (e0 != cudaSuccess) return e0;
     dim3 grid((unsigned)max_parts, (unsigned)n_songs);
     pass1_kernel<KIND, FULL><<<grid, kP1Threads, bytes, st>>>(p);
     return cudaGetLastError();

@@ -26,7 +26,10 @@ static int analyse_song(struct bl_song const *const song, unsigned what, blx_res
 int bl_analyze(char const *const filename, struct bl_song *current_song) {
     if (bl_audio_decode(filename, current_song) == BL_OK) {
         blx_result r;
-        if (analyse_song(current_song, BLX_DO_ALL, &r) != BL_OK) return BL_UNEXPECTED;
+        if (analyse_song(current_song, BLX_DO_ALL, &r) != BL_OK) {
+            bl_free_song(current_song); /* nothing to rate: do not leave the decoded PCM behind */
+            return BL_UNEXPECTED;
+        }
         current_song->force_vector.tempo = r.tempo;
         current_song->force_vector.amplitude = r.amplitude;
         current_song->force_vector.frequency = r.frequency;
@@ -35,6 +38,7 @@ int bl_analyze(char const *const filename, struct bl_song *current_song) {
         current_song->calm_or_loud = r.calm_or_loud;
         if (r.status != 0) {
             fprintf(stderr, "bliss: song cannot be rated (status 0x%x: too short, silent or constant)\n", r.status);
+            bl_free_song(current_song);
             return BL_UNEXPECTED;
         }
         return current_song->calm_or_loud;

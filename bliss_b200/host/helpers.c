@@ -10,29 +10,60 @@
 #include "../../include/bliss.h"
 #include "engine_singleton.h"
 
+/* A small pool of engines (one per concurrent caller, each with its own streams and device buffers): bl_analyze
+ * and the stand-alone analysers may be called from several threads at once - unlike the reference, whose fftw
+ * planner calls make that unsafe (reference src/tempo_atk_sort.c:94,295) - and their kernels then overlap on the
+ * GPU. The mutex only guards the pool's free list; no caller holds it while it analyses. */
+#define BL_POOL_MAX 16
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
-static blx_engine *g_engine = NULL;
-static int g_failed = 0;
+static pthread_cond_t g_freed = PTHREAD_COND_INITIALIZER;
+static blx_engine *g_pool[BL_POOL_MAX];
+static int g_busy[BL_POOL_MAX];
+static int g_created = 0, g_failed = 0;
+static __thread int t_slot = -1; /* the engine this thread holds between acquire and release */
 
 blx_engine *bl_engine_acquire(void) {
     pthread_mutex_lock(&g_lock);
-    if (!g_engine && !g_failed) {
-        const char *dev = getenv("BLISS_DEVICE");
-        int rc = blx_init(dev ? atoi(dev) : 0, &g_engine);
-        if (rc != BLX_OK) {
-            fprintf(stderr, "bliss: cannot start the GPU engine: %s\n", blx_last_error());
-            g_engine = NULL;
-            g_failed = 1;
+    for (;;) {
+        if (g_failed) break;
+        int free_slot = -1;
+        for (int i = 0; i < g_created; ++i)
+            if (!g_busy[i]) { free_slot = i; break; }
+        if (free_slot < 0 && g_created < BL_POOL_MAX) {
+            const char *dev = getenv("BLISS_DEVICE");
+            blx_engine *e = NULL;
+            /* created under the lock: engine start-up is rare and blx_init sets per-device kernel attributes */
+            if (blx_init(dev ? atoi(dev) : 0, &e) != BLX_OK) {
+                if (g_created == 0) {
+                    fprintf(stderr, "bliss: cannot start the GPU engine: %s\n", blx_last_error());
+                    g_failed = 1;
+                    break;
+                }
+            } else {
+                g_pool[g_created] = e;
+                g_busy[g_created] = 0;
+                free_slot = g_created++;
+            }
         }
+        if (free_slot >= 0) {
+            g_busy[free_slot] = 1;
+            t_slot = free_slot;
+            pthread_mutex_unlock(&g_lock);
+            return g_pool[free_slot];
+        }
+        pthread_cond_wait(&g_freed, &g_lock); /* BL_POOL_MAX callers are inside already */
     }
-    if (!g_engine) {
-        pthread_mutex_unlock(&g_lock);
-        return NULL;
-    }
-    return g_engine;
+    pthread_mutex_unlock(&g_lock);
+    return NULL;
 }
 
-void bl_engine_release(void) { pthread_mutex_unlock(&g_lock); }
+void bl_engine_release(void) {
+    pthread_mutex_lock(&g_lock);
+    if (t_slot >= 0) g_busy[t_slot] = 0;
+    t_slot = -1;
+    pthread_cond_signal(&g_freed);
+    pthread_mutex_unlock(&g_lock);
+}
 
 void bl_free_song(struct bl_song *const song) {
     free(song->artist);

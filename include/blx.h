@@ -144,6 +144,29 @@ int blx_distance_rows_device(blx_engine *e, const float *d_vectors, int n, int r
 int blx_distance_nearest_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows,
                                 int *d_nearest_index, float *d_nearest_dist, double *d_row_sum, void *stream);
 
+/* ---- several GPUs from one C process ---------------------------------------------
+ * BASELINE.json configs[2] / configs[4] without Python: one engine + one host thread per device. Songs shard in
+ * contiguous blocks (device r analyses [r N / G, (r + 1) N / G)), no data-path collective; the force vectors of
+ * every block stay resident on its device. blx_multi_nearest all-gathers them device to device (ncclAllGather over
+ * NVLink; peer copies if NCCL cannot start - blx_multi_transport says which) and reduces every device's rows
+ * against all columns: nearest other song per song, with the bl_distance semantics of blx_distance_nearest_device.
+ * devices == NULL: the first n_devices visible devices (n_devices <= 0: all). */
+typedef struct blx_multi blx_multi;
+int blx_multi_init(const int *devices, int n_devices, blx_multi **out);
+void blx_multi_shutdown(blx_multi *m);
+int blx_multi_device_count(blx_multi *m);
+const char *blx_multi_transport(blx_multi *m);
+blx_engine *blx_multi_engine(blx_multi *m, int rank);
+int blx_multi_analyze_batch_s16(blx_multi *m, const int16_t *const *pcm, const int *n_samples, const int *channels,
+                                const uint64_t *duration_s, int n_songs, unsigned what, blx_result *out);
+int blx_multi_analyze_batch_f32(blx_multi *m, const float *const *pcm, const int64_t *n_in, int n_songs, unsigned what,
+                                blx_result *out);
+/* Replaces the resident vectors by n host vectors (n x 4 floats), sharded the same way. */
+int blx_multi_set_vectors(blx_multi *m, const float *vectors, int n);
+/* All-gather + all-pairs nearest neighbour over the resident vectors; host outputs of n entries (either may be
+ * NULL); gather_ms / nearest_ms (may be NULL): device time of the two phases, max over devices. */
+int blx_multi_nearest(blx_multi *m, int *nearest_index, float *nearest_dist, float *gather_ms, float *nearest_ms);
+
 /* ---- small reference helpers on the device --------------------------------------
  * bl_mean / bl_variance (reference src/helpers.c:30-49) and bl_rectangular_filter
  * (reference src/tempo_atk_sort.c:19-40), host buffers. */

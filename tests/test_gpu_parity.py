@@ -594,3 +594,40 @@ def test_sub_batches_and_pipelined_calls_are_byte_identical(engine):
             assert copy.cpu().numpy().tobytes() == want
         finally:
             small.close()
+
+
+def test_bl_analyze_from_many_threads(oracle):
+    """The drop-in wrappers take an engine out of a pool per call: eight threads analysing at once (the reference is not
+    thread-safe at all, reference src/tempo_atk_sort.c:94,295) all get the single-threaded record, byte for byte."""
+    import threading
+    L = bliss_b200.load()
+    flac = os.path.join(GOLDEN_DIR, "song.flac").encode()
+
+    def analyse():
+        s = bliss_b200.BlSong()
+        rc = L.bl_analyze(flac, ctypes.byref(s))
+        rec = (rc, s.force, s.force_vector.tempo, s.force_vector.amplitude, s.force_vector.frequency, s.force_vector.attack,
+               s.nSamples, s.calm_or_loud)
+        env = bliss_b200.EnvelopeResult()
+        L.bl_envelope_sort(ctypes.byref(s), ctypes.byref(env))
+        rec += (env.tempo, env.attack, L.bl_amplitude_sort(ctypes.byref(s)), L.bl_frequency_sort(ctypes.byref(s)))
+        L.bl_free_song(ctypes.byref(s))
+        return rec
+
+    want = analyse()
+    assert want[0] == 1 and want[8:] == (want[2], want[5], want[3], want[4])
+    got, errs = [], []
+
+    def worker():
+        try:
+            for _ in range(3):
+                got.append(analyse())
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    threads = [threading.Thread(target=worker) for _ in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs and len(got) == 24 and all(g == want for g in got)

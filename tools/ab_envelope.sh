@@ -26,7 +26,7 @@ else
   for so in $VAR/libbliss_*.so; do
     v=$(basename $so .so)
     BLISS_B200_LIB=$PWD/$so python bench.py --steps 3 --warmup 2 --songs-per-step $songs --no-cpu --no-spectral --no-distance \
-      --e2e-songs 2 --s16-songs 128 --parity-songs 0 --chain-songs 0 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || echo "$v FAILED"
+      --e2e-songs 2 --s16-songs 128 --parity-songs 0 --chain-songs 0 --no-bl-analyze > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || echo "$v FAILED"
     python - "$v" gpurun_out/ab_$v.json <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
