@@ -59,7 +59,7 @@ BLX_H_SYMBOLS = [
     "blx_device_count", "blx_init", "blx_shutdown", "blx_last_error", "blx_configure", "blx_configure_sub_batch", "blx_debug_flags",
     "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_device", "blx_analyze_device_async", "blx_join",
     "blx_spectral_device",
-    "blx_distance_matrix", "blx_cosine_matrix", "blx_distance_rows_device", "blx_distance_nearest_device",
+    "blx_distance_matrix", "blx_cosine_matrix", "blx_distance_rows_device", "blx_distance_nearest_device", "blx_cosine_nearest_device",
     "blx_mean_variance_s16", "blx_rectangular_filter", "blx_frontend_f32", "blx_resample_to_s16", "blx_envelope_energy_s16",
     "blx_frequency_spectrum_s16", "blx_histogram_s16", "blx_envelope_tail", "blx_envelope_energy_f32",
     "blx_profile_enable", "blx_profile_reset", "blx_profile_read", "blx_kernel_name", "blx_launch_count",
@@ -116,6 +116,8 @@ def load():
     L.blx_distance_rows_device.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     L.blx_distance_nearest_device.restype = ctypes.c_int
     L.blx_distance_nearest_device.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    L.blx_cosine_nearest_device.restype = ctypes.c_int
+    L.blx_cosine_nearest_device.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     L.blx_mean_variance_s16.restype = ctypes.c_int
     L.blx_mean_variance_s16.argtypes = [vp, c_i16p, ctypes.c_int, c_i32p, c_i32p, c_i32p]
     L.blx_rectangular_filter.restype = ctypes.c_int

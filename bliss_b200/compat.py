@@ -175,12 +175,13 @@ def version():
     return L.load().bl_version()
 
 
-def playlist(engine, vectors, seed_index, k=None):
-    """Songs ordered by bl_distance to song `seed_index` (the seed itself first, distance 0).
+def playlist(engine, vectors, seed_index, k=None, metric="euclidean"):
+    """Songs ordered by bl_distance to song `seed_index` (the seed itself first, distance 0), or, with
+    metric="cosine", by decreasing bl_cosine_similarity (reference src/analyze.c:127-145).
 
-    `vectors`: (n, 4) float32 [tempo, amplitude, frequency, attack]. The n distances are one row of the
-    all-pairs kernel (bit-identical to bl_distance); ties keep index order. Returns (indices, distances)
-    as numpy arrays, cut to the first k if given."""
+    `vectors`: (n, 4) float32 [tempo, amplitude, frequency, attack]. The n values are one row of the
+    all-pairs kernel (bit-identical to the reference's scalar functions); ties keep index order. Returns
+    (indices, values) as numpy arrays, cut to the first k if given."""
     import torch
     v = torch.as_tensor(np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, 4)).cuda()
     n = v.shape[0]
@@ -188,8 +189,11 @@ def playlist(engine, vectors, seed_index, k=None):
         raise IndexError(seed_index)
     row = torch.empty(n, dtype=torch.float32, device=v.device)
     st = torch.cuda.current_stream(v.device).cuda_stream
-    engine.distance_rows_device(v.data_ptr(), n, int(seed_index), 1, row.data_ptr(), stream=st)
-    order = torch.argsort(row, stable=True)
+    cosine = metric == "cosine"
+    if not cosine and metric != "euclidean":
+        raise ValueError(metric)
+    engine.distance_rows_device(v.data_ptr(), n, int(seed_index), 1, row.data_ptr(), cosine=cosine, stream=st)
+    order = torch.argsort(row, stable=True, descending=cosine)
     if k is not None:
         order = order[:k]
     return order.cpu().numpy(), row[order].cpu().numpy()

@@ -259,6 +259,64 @@ cudaError_t launch_distance_nearest(const float *d_vectors, int n, int row0, int
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- fused epilogue, cosine similarity
+// Most similar other song under bl_cosine_similarity (reference src/analyze.c:127-145), nothing materialised:
+// per row the column with the largest similarity, the lowest index among equal floats - what a scan over the
+// reference's values gives. The exact value needs two double square roots' product and a double division per pair;
+// a float estimate (dot * 1/|a| * 1/|b|, within 2e-6 of the exact value) sorts out every column that cannot reach
+// the row's current best, so the exact expression runs for a handful of candidates per row only.
+namespace {
+constexpr int kCosTile = 1024;
+struct CosCol { float4 b; float rn; float pad; double sn; }; // vector, 1 / |b| (float), |b| (double)
+}
+
+__global__ void __launch_bounds__(kDistThreads) cosine_nearest_kernel(const float4 *__restrict__ v, int n, int row0, int n_rows,
+                                                                      int *__restrict__ idx_out, float *__restrict__ sim_out) {
+    __shared__ CosCol cols[kCosTile];
+    const int lr = blockIdx.x * kDistThreads + threadIdx.x;
+    const int row = (lr < n_rows) ? row0 + lr : -1;
+    const float4 a = (row >= 0) ? v[row] : make_float4(1, 0, 0, 0);
+    const double sa = __dsqrt_rn((double)sqnorm(a));
+    const float rna = (float)(1.0 / sa);
+    float best = -__int_as_float(0x7f800000);
+    int best_j = -1;
+    for (int c0 = 0; c0 < n; c0 += kCosTile) {
+        const int cn = min(kCosTile, n - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += kDistThreads) {
+            const float4 b = v[c0 + i];
+            const double sn = __dsqrt_rn((double)sqnorm(b));
+            cols[i].b = b; cols[i].sn = sn; cols[i].rn = (float)(1.0 / sn); cols[i].pad = 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < cn; ++i) {
+            const float4 b = cols[i].b;
+            float dot = __fmul_rn(a.x, b.x);
+            dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
+            dot = __fadd_rn(dot, __fmul_rn(a.z, b.z));
+            dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
+            const float est = dot * rna * cols[i].rn;
+            // !(est + margin < best) also lets NaN estimates through (zero vectors: the exact value is NaN and never wins)
+            if (!(est + 4e-6f < best) && c0 + i != row) {
+                const float c = __double2float_rn(__ddiv_rn((double)dot, __dmul_rn(sa, cols[i].sn)));
+                if (c > best) { best = c; best_j = c0 + i; }
+            }
+        }
+    }
+    if (row >= 0) {
+        if (idx_out) idx_out[row - row0] = best_j;
+        if (sim_out) sim_out[row - row0] = best;
+    }
+}
+
+cudaError_t launch_cosine_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_sim, cudaStream_t st) {
+    if (n <= 0 || n_rows <= 0) return cudaSuccess;
+    cosine_nearest_kernel<<<(unsigned)((n_rows + kDistThreads - 1) / kDistThreads), kDistThreads, 0, st>>>(
+        reinterpret_cast<const float4 *>(d_vectors), n, row0, n_rows, d_idx, d_sim);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- stand-alone front-end
 // blx_frontend.h, one thread per output frame. Used by blx_frontend_f32 (tests, decode of 44.1 kHz
 // files); the analysis path runs the same arithmetic fused into pass 1.

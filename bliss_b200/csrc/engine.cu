@@ -720,6 +720,17 @@ extern "C" int blx_distance_nearest_device(blx_engine *e, const float *d_vectors
     return BLX_OK;
 }
 
+extern "C" int blx_cosine_nearest_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows, int *d_index,
+                                         float *d_similarity, void *stream) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!d_vectors || n < 0 || row0 < 0 || n_rows < 0 || row0 + n_rows > n) return fail(BLX_ERR_ARG, "bad distance arguments");
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->compute;
+    ProfScope ps(e, BLX_K_DISTANCE, st);
+    CK(launch_cosine_nearest(d_vectors, n, row0, n_rows, d_index, d_similarity, st));
+    return BLX_OK;
+}
+
 static int matrix_host(blx_engine *e, const float *vectors, int n, float *out, int mode) {
     int rc = check_engine(e);
     if (rc) return rc;

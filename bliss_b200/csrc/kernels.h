@@ -64,6 +64,7 @@ cudaError_t launch_distance_rows(const float *d_vectors, int n, int row0, int n_
 int distance_nearest_splits(int n, int n_rows, bool with_sum);
 cudaError_t launch_distance_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_dist,
                                     double *d_sum, unsigned long long *d_packed, int splits, cudaStream_t st);
+cudaError_t launch_cosine_nearest(const float *d_vectors, int n, int row0, int n_rows, int *d_idx, float *d_sim, cudaStream_t st);
 cudaError_t launch_rect_filter(double *d_out, const double *d_in, int n, int width, cudaStream_t st);
 // decode-stage resampler (include/blx_resample.h): in = the reader's int32 samples (interleaved), out = int16 stereo
 struct ResampleParams {

@@ -25,6 +25,15 @@ class BlxError(RuntimeError):
     pass
 
 
+def _stream_arg(stream):
+    """cudaStream_t for the C-ABI. None = the engine's own stream. A handle of 0 is CUDA's legacy default stream (what
+    torch.cuda.current_stream().cuda_stream returns outside a stream context): it is passed as cudaStreamLegacy (0x1),
+    because NULL already means "the engine's own stream" - the work must be ordered with the caller's stream, not beside it."""
+    if stream is None:
+        return None
+    return ctypes.c_void_p(int(stream) or 1)
+
+
 class Engine:
     def __init__(self, device=0, chunk_bytes=None):
         self._lib = L.load()
@@ -106,11 +115,11 @@ class Engine:
         chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
         f = self._lib.blx_analyze_device if wait else self._lib.blx_analyze_device_async
         self._ck(f(self._h, fmt, ctypes.c_void_p(int(d_pcm)), offs, lens, chs, durs, n, what, ctypes.c_void_p(int(d_out)),
-                   ctypes.c_void_p(int(stream)) if stream else None))
+                   _stream_arg(stream)))
 
     def join(self, stream=None):
         """Makes `stream` wait for every analysis enqueued so far (after analyze_device(..., wait=False))."""
-        self._ck(self._lib.blx_join(self._h, ctypes.c_void_p(int(stream)) if stream else None))
+        self._ck(self._lib.blx_join(self._h, _stream_arg(stream)))
 
     def spectral_device(self, fmt, d_pcm, offsets, lengths, d_frequency, channels=None, stream=None):
         n = len(offsets)
@@ -119,7 +128,7 @@ class Engine:
         chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
         self._ck(self._lib.blx_spectral_device(self._h, fmt, ctypes.c_void_p(int(d_pcm)), offs, lens, chs, n,
                                                ctypes.c_void_p(int(d_frequency)),
-                                               ctypes.c_void_p(int(stream)) if stream else None))
+                                               _stream_arg(stream)))
 
     # ------------------------------------------------------------------ distances
     def distance_matrix(self, vectors, cosine=False):
@@ -132,13 +141,18 @@ class Engine:
     def distance_rows_device(self, d_vectors, n, row0, n_rows, d_out, cosine=False, stream=None):
         self._ck(self._lib.blx_distance_rows_device(self._h, ctypes.c_void_p(int(d_vectors)), n, row0, n_rows,
                                                     1 if cosine else 0, ctypes.c_void_p(int(d_out)),
-                                                    ctypes.c_void_p(int(stream)) if stream else None))
+                                                    _stream_arg(stream)))
 
     def distance_nearest_device(self, d_vectors, n, row0, n_rows, d_index, d_dist, d_sum, stream=None):
         self._ck(self._lib.blx_distance_nearest_device(
             self._h, ctypes.c_void_p(int(d_vectors)), n, row0, n_rows,
             ctypes.c_void_p(int(d_index)) if d_index else None, ctypes.c_void_p(int(d_dist)) if d_dist else None,
-            ctypes.c_void_p(int(d_sum)) if d_sum else None, ctypes.c_void_p(int(stream)) if stream else None))
+            ctypes.c_void_p(int(d_sum)) if d_sum else None, _stream_arg(stream)))
+
+    def cosine_nearest_device(self, d_vectors, n, row0, n_rows, d_index, d_similarity, stream=None):
+        self._ck(self._lib.blx_cosine_nearest_device(
+            self._h, ctypes.c_void_p(int(d_vectors)), n, row0, n_rows, ctypes.c_void_p(int(d_index)) if d_index else None,
+            ctypes.c_void_p(int(d_similarity)) if d_similarity else None, _stream_arg(stream)))
 
     # ------------------------------------------------------------------ helpers
     def mean_variance(self, pcm, mean_in=None):

@@ -100,8 +100,8 @@ int blx_analyze_batch_f32(blx_engine *e, const float *const *pcm, const int64_t 
  * d_pcm: device pointer (BLX_FMT_S16: int16_t*, BLX_FMT_F32: float*). offsets/lengths
  * are HOST arrays in elements; channels (S16 only, NULL => 2) and duration_s (S16 only;
  * F32 derives it) are HOST arrays. d_out: DEVICE array of n_songs blx_result.
- * stream: a cudaStream_t passed as void* (NULL = the engine's own stream). The call
- * only enqueues work; it does not synchronise. The kernels run on the engine's own streams (sub-batches of 512
+ * stream: a cudaStream_t passed as void* (NULL = the engine's own stream; for CUDA's legacy default stream,
+ * whose handle is also 0, pass cudaStreamLegacy = (void *)1). The call only enqueues work; it does not synchronise. The kernels run on the engine's own streams (sub-batches of 512
  * songs; the sequential tail of one under the envelope kernel of the next), fenced against `stream` on both
  * sides: work enqueued on `stream` before the call is seen, work enqueued after it sees the results. */
 int blx_analyze_device(blx_engine *e, int fmt, const void *d_pcm, const int64_t *offsets,
@@ -143,6 +143,12 @@ int blx_distance_rows_device(blx_engine *e, const float *d_vectors, int n, int r
  * such call per engine in flight at a time (calls on one stream are ordered anyway). */
 int blx_distance_nearest_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows,
                                 int *d_nearest_index, float *d_nearest_dist, double *d_row_sum, void *stream);
+
+/* The same for bl_cosine_similarity (reference src/analyze.c:127-145): per row of the slab the MOST similar other
+ * song - the largest similarity as the reference's scalar code rounds it, the lowest index among equal values.
+ * Either output may be NULL. */
+int blx_cosine_nearest_device(blx_engine *e, const float *d_vectors, int n, int row0, int n_rows, int *d_index,
+                              float *d_similarity, void *stream);
 
 /* ---- several GPUs from one C process ---------------------------------------------
  * BASELINE.json configs[2] / configs[4] without Python: one engine + one host thread per device. Songs shard in

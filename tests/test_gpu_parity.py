@@ -631,3 +631,63 @@ def test_bl_analyze_from_many_threads(oracle):
     for t in threads:
         t.join()
     assert not errs and len(got) == 24 and all(g == want for g in got)
+
+
+def test_default_stream_is_ordered_with_the_callers_work(engine):
+    """torch.cuda.current_stream().cuda_stream is 0 on the legacy default stream; the binding must run the kernel ON that
+    stream (cudaStreamLegacy), not on the engine's own: a slow producer in front and a consumer behind see ordinary
+    stream order without any synchronize in between."""
+    import torch
+    from bliss_b200 import parallel
+    rng = np.random.default_rng(5)
+    v = (rng.standard_normal((4096, 4)) * 9).astype(np.float32)
+    want_idx, want_dst = parallel.nearest_neighbours(engine, torch.from_numpy(v).cuda())
+    torch.cuda.synchronize()
+    want_idx, want_dst = want_idx.cpu().numpy(), want_dst.cpu().numpy()
+    assert torch.cuda.current_stream().cuda_stream == 0
+    a = torch.randn(6144, 6144, device="cuda")
+    staged = torch.from_numpy(v).cuda()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        table = torch.zeros(4096, 4, device="cuda")
+        b = a
+        for _ in range(6):
+            b = b @ a  # tens of milliseconds of work queued in front of the copy below
+        table.copy_(staged)  # the real vectors arrive only after the matmuls
+        idx, dst = parallel.nearest_neighbours(engine, table)
+        got_idx, got_dst = idx.cpu().numpy(), dst.cpu().numpy()  # .cpu() waits on the default stream only
+        assert np.array_equal(got_idx, want_idx) and np.array_equal(got_dst, want_dst)
+        del b
+
+
+def test_cosine_nearest_matches_cosine_matrix(engine, oracle):
+    """Fused cosine epilogue: per row the most similar other song = argmax over the (bit-exact) cosine matrix, lowest index on
+    ties, including exact duplicates, scaled copies (similarity rounds to 1.0 for several columns) and a zero vector (NaN)."""
+    import torch
+    rng = np.random.default_rng(44)
+    v = (rng.standard_normal((2500, 4)) * np.array([6, 4, 9, 7])).astype(np.float32)
+    v[100] = v[2000]
+    v[300] = v[2000] * 2.0       # same direction, different length
+    v[301] = v[2000] * 0.5
+    v[777] = 0.0                 # |v| = 0: every similarity with it is NaN and never wins
+    c = engine.distance_matrix(v, cosine=True)
+    assert c[3, 9] == np.float32(oracle.cosine_similarity(v[3], v[9]))
+    dv = torch.from_numpy(v).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    for row0, nr in ((0, 2500), (1990, 300)):
+        idx = torch.full((nr,), -7, dtype=torch.int32, device="cuda")
+        sim = torch.zeros(nr, dtype=torch.float32, device="cuda")
+        engine.cosine_nearest_device(dv.data_ptr(), 2500, row0, nr, idx.data_ptr(), sim.data_ptr(), stream=st)
+        gi, gs = idx.cpu().numpy(), sim.cpu().numpy()
+        for r in range(nr):
+            i = row0 + r
+            if i == 777:
+                assert gi[r] == -1
+                continue
+            rowv = c[i].astype(np.float64).copy()
+            rowv[i] = -np.inf
+            rowv[np.isnan(rowv)] = -np.inf
+            assert gs[r] == np.float32(rowv.max()) and gi[r] == int(np.argmax(rowv)), (i, gi[r], gs[r], int(np.argmax(rowv)), rowv.max())
+    from bliss_b200 import compat as bliss
+    order, vals = bliss.playlist(engine, v, 2000, k=6, metric="cosine")
+    assert set(order[:4].tolist()) == {100, 300, 301, 2000} and np.all(vals[:4] >= np.float32(0.9999999))
