@@ -744,19 +744,30 @@ def run_ours(args):
         o16, l16 = [i * stride16 for i in range(Bn)], [n16] * Bn
         durs = [int(args.seconds)] * Bn
         d_out16 = torch.zeros(Bn * 8, dtype=torch.int32, device=dev)
+        def step16():
+            eng.analyze_device(E.FMT_S16, s16.data_ptr(), o16, l16, d_out16.data_ptr(), durations=durs, stream=stream, wait=False)
         for _ in range(3):
-            eng.analyze_device(E.FMT_S16, s16.data_ptr(), o16, l16, d_out16.data_ptr(), durations=durs, stream=stream)
+            step16()
+        eng.join(stream)
+        eng.profile(True)
+        eng.profile_reset()
         barrier()
         ev0.record()
         for _ in range(3):
-            eng.analyze_device(E.FMT_S16, s16.data_ptr(), o16, l16, d_out16.data_ptr(), durations=durs, stream=stream)
+            step16()
+        eng.join(stream)
         ev1.record()
         barrier()
         ms16 = max_over_ranks(ev0.elapsed_time(ev1)) / 3
+        p16 = eng.profile_read()
+        eng.profile(False)
         r16 = np.frombuffer(d_out16.cpu().numpy().tobytes(), dtype=bliss_b200.RESULT_DTYPE)
         native = {"workload": f"{Bn} x {args.seconds:g}-s int16 / 22 050 Hz / stereo songs per GPU (the reference decoder's output "
                               "format), full pipeline", "value": world * Bn / (ms16 * 1e-3), "unit": UNIT, "ms_per_pass": ms16,
-                  "bytes_per_song": n16 * 2, "all_status_ok": bool(np.all(r16["status"] == 0))}
+                  "bytes_per_song": n16 * 2, "all_status_ok": bool(np.all(r16["status"] == 0)),
+                  "kernel_ms_per_pass": {k: v[0] / 3 for k, v in p16.items() if v[1]},
+                  "envelope_frac_fp64": (FP64_FLOP_PER_HOP * hops * Bn / (p16["envelope_kernel"][0] / 3 * 1e-3) / 1e12 / fp64_peak)
+                  if p16.get("envelope_kernel", (0, 0))[1] else None}
         del s16
 
     # ---------------- configs[3]/[4]: all-pairs bl_distance over 1 M force vectors, fused nearest-neighbour
@@ -911,7 +922,7 @@ def main():
     ap.add_argument("--songs-per-step", type=int, default=2048)
     ap.add_argument("--seconds", type=float, default=180.0)
     ap.add_argument("--e2e-songs", type=int, default=256)
-    ap.add_argument("--s16-songs", type=int, default=256)
+    ap.add_argument("--s16-songs", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spectral", action="store_true")
     ap.add_argument("--no-distance", action="store_true")

@@ -315,7 +315,22 @@ __device__ __forceinline__ double grid_to_double(int ex, unsigned q) {
 // that fails (a prefix sum within rounding noise of a power of two; sums that are not normal floats) is
 // redone by the binade-by-binade scan above. Host model and test against the sequential chain:
 // tools/chain_model4.c.
-__device__ __forceinline__ double float_chain(const double *xr, int lane16, bool active, bool force_slow) {
+#ifndef BLX_ENV_CVT_MAGIC
+#define BLX_ENV_CVT_MAGIC 0 // 1: int -> double by a magic-constant add (ALU + FP64 pipes) instead of I2F.F64 (conversion pipe)
+#endif
+#ifndef BLX_ENV_CHAIN_G
+#define BLX_ENV_CHAIN_G 4 // bins per group of the accumulation (4 or 2)
+#endif
+// scratch behind the spectrum rows of a hop's exchange buffer: per lane and group {clean bins in front, exponents}
+constexpr int kAuxOff = kPRow * 16;          // doubles
+constexpr int kAuxLaneStride = 10;           // doubles per lane (8 used for G = 2): 80-byte rows, conflict-free 128-bit stores
+static_assert((kAuxOff + 16 * kAuxLaneStride) * 8 <= kXchgElems * 16, "scratch fits behind the spectrum");
+
+template <int G>
+__device__ __forceinline__ double float_chain(double *xr, int lane16, bool active, bool force_slow) {
+    constexpr int NG = 16 / G;                     // groups per lane
+    constexpr int kWords = 16 * NG / 32;           // 32-bit words of one half-warp's dirty mask
+    constexpr int kLanesPerWord = 32 / NG;
     const unsigned full = 0xffffffffu;
     const int hw = (threadIdx.x >> 4) & 1;
     double pv[16];
@@ -331,14 +346,16 @@ __device__ __forceinline__ double float_chain(const double *xr, int lane16, bool
         r16 = (double)sf;
     }
     r16 = __shfl_sync(full, r16, 0, 16);
-    // exact prefix sums in double: local, then across the half-warp
-    double c3, c7, c11, inc;
+    // exact prefix sums in double: local (kept at the group boundaries), then across the half-warp
+    double cb[NG], inc;
     {
         double c = pv[0] + (lane16 == 0 ? p0 : 0.0);
-        c += pv[1]; c += pv[2]; c += pv[3]; c3 = c;
-        c += pv[4]; c += pv[5]; c += pv[6]; c += pv[7]; c7 = c;
-        c += pv[8]; c += pv[9]; c += pv[10]; c += pv[11]; c11 = c;
-        c += pv[12]; c += pv[13]; c += pv[14]; c += pv[15];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            if (i % G == 0) cb[i / G - 1] = c;
+            c += pv[i];
+        }
+        cb[NG - 1] = c;
         inc = c;
     }
 #pragma unroll
@@ -352,26 +369,24 @@ __device__ __forceinline__ double float_chain(const double *xr, int lane16, bool
     // chain ends at r16. (Without this a silent hop, whose sum never becomes a normal float, would take the
     // slow path one bin at a time.)
     const bool rest_zero = __shfl_sync(full, inc, 15, 16) == __shfl_sync(full, inc, 0, 16);
-    // the four groups: exponent of S at the boundaries, clean groups summed at their grid
+    // the groups: exponent of S at the boundaries, clean groups summed at their grid
     const bool mine = active && lane16 != 0;
-    int h[5];
+    int h[NG + 1];
     h[0] = __double2hiint(excl);
-    h[1] = __double2hiint(excl + c3);
-    h[2] = __double2hiint(excl + c7);
-    h[3] = __double2hiint(excl + c11);
-    h[4] = __double2hiint(inc);
-    unsigned before[4], pack[4], dirty = 0, run = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NG - 1; ++j) h[j + 1] = __double2hiint(excl + cb[j]);
+    h[NG] = __double2hiint(inc);
+    unsigned before[NG], dirty = 0, run = 0;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
         const double M = __hiloint2double((h[j] & 0x7FF00000) + 0x1D80000, 0); // 1.5 * 2^(e + 29): ulp = float grid of binade e
         unsigned g = 0;
 #pragma unroll
-        for (int i = 4 * j; i < 4 * j + 4; ++i) g += (unsigned)__double2loint(pv[i] + M);
+        for (int i = G * j; i < G * j + G; ++i) g += (unsigned)__double2loint(pv[i] + M);
         const bool d = mine && (((h[j] ^ h[j + 1]) & 0x7FF00000) != 0);
         before[j] = run;
         run += (d || !mine) ? 0u : g;
         dirty |= d ? (1u << j) : 0u;
-        pack[j] = ((unsigned)h[j] >> 20) | (((unsigned)h[j + 1] >> 20) << 16); // exponents in front of / behind the group
     }
     unsigned incI = run;
 #pragma unroll
@@ -381,44 +396,67 @@ __device__ __forceinline__ double float_chain(const double *xr, int lane16, bool
     }
     const unsigned baseI = incI - run;
     const unsigned total = __shfl_sync(full, incI, 15, 16);
-    const int e_end = __shfl_sync(full, h[4], 15, 16) >> 20;
-    // the dirty groups of this half-warp, bit 4 b + j, as two words (lanes 0..7, lanes 8..15)
-    unsigned m_lo, m_hi;
+    const int e_end = __shfl_sync(full, h[NG], 15, 16) >> 20;
+    // per lane and group: clean bins in front of the group, exponents in front of / behind it (read back by the
+    // half-warp for the dirty groups only)
     {
-        const unsigned bits = dirty << (4 * (lane16 & 7));
-        const int word = 2 * hw + (lane16 >> 3);
-        const unsigned w0 = __reduce_or_sync(full, word == 0 ? bits : 0u), w1 = __reduce_or_sync(full, word == 1 ? bits : 0u);
-        const unsigned w2 = __reduce_or_sync(full, word == 2 ? bits : 0u), w3 = __reduce_or_sync(full, word == 3 ? bits : 0u);
-        m_lo = hw ? w2 : w0;
-        m_hi = hw ? w3 : w1;
+        uint2 *aux = reinterpret_cast<uint2 *>(xr + kAuxOff + kAuxLaneStride * lane16);
+#pragma unroll
+        for (int j = 0; j < NG; j += 2) {
+            const uint4 t = make_uint4(baseI + before[j], ((unsigned)h[j] >> 20) | (((unsigned)h[j + 1] >> 20) << 16),
+                                       baseI + before[j + 1], ((unsigned)h[j + 1] >> 20) | (((unsigned)h[j + 2] >> 20) << 16));
+            *reinterpret_cast<uint4 *>(aux + j) = t;
+        }
     }
+    // the dirty groups of this half-warp, bit NG b + j, as kWords words
+    unsigned mk[kWords];
+    {
+        const unsigned bits = dirty << (NG * (lane16 % kLanesPerWord));
+        const int word = kWords * hw + lane16 / kLanesPerWord;
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) {
+            const unsigned lo = __reduce_or_sync(full, word == w ? bits : 0u), hi = __reduce_or_sync(full, word == kWords + w ? bits : 0u);
+            mk[w] = hw ? hi : lo;
+        }
+    }
+    __syncwarp(full); // scratch visible
     // the dirty groups in order; both half-warps step together (the one that runs out idles)
     int ex = (__double2hiint(r16) >> 20) & 0x7ff;
     unsigned q = (((unsigned)__double2hiint(r16) & 0xFFFFFu) << 3) | ((unsigned)__double2loint(r16) >> 29) | 0x800000u;
     bool ok = !active || (ex >= 1023 - 126 && ex <= 1023 + 126);
     unsigned Pprev = 0;
-    while (__any_sync(full, (m_lo | m_hi) != 0u)) {
-        const bool act = (m_lo | m_hi) != 0u;
-        const int bit = m_lo ? (__ffs(m_lo) - 1) : (m_hi ? 32 + (__ffs(m_hi) - 1) : 4); // idle: lane 1, group 0
-        if (m_lo) m_lo &= m_lo - 1;
-        else m_hi &= m_hi - 1;
-        const int b = bit >> 2, j = bit & 3;
-        const unsigned bsel = (j & 2) ? ((j & 1) ? before[3] : before[2]) : ((j & 1) ? before[1] : before[0]);
-        const unsigned psel = (j & 2) ? ((j & 1) ? pack[3] : pack[2]) : ((j & 1) ? pack[1] : pack[0]);
-        const unsigned Pb = __shfl_sync(full, baseI + bsel, b, 16);
-        const unsigned pk = __shfl_sync(full, psel, b, 16);
-        // the group's four bins (row b, elements 4 j .. 4 j + 3)
+    for (;;) {
+        unsigned any = mk[0];
+#pragma unroll
+        for (int w = 1; w < kWords; ++w) any |= mk[w];
+        if (!__any_sync(full, any != 0u)) break;
+        const bool act = any != 0u;
+        int bit = NG; // idle: lane 1, group 0
+        bool found = false;
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) {
+            const bool take = !found && mk[w] != 0u;
+            if (take) { bit = 32 * w + (__ffs(mk[w]) - 1); mk[w] &= mk[w] - 1; }
+            found = found || take;
+        }
+        const int b = bit / NG, j = bit % NG;
+        const uint2 rec = *reinterpret_cast<const uint2 *>(xr + kAuxOff + kAuxLaneStride * b + j);
+        const unsigned Pb = rec.x, pk = rec.y;
+        // the group's bins (row b, elements G j .. G j + G - 1)
         const double2 *row = reinterpret_cast<const double2 *>(xr + kPRow * b);
-        const double2 pa = row[2 * j], pb = row[2 * j + 1], pc = row[8];
-        const double p3 = (j == 3 && b <= 6) ? pc.y : pb.y;
+        double pg[G];
+        {
+            const double2 pa = row[(G / 2) * j], pc = row[8];
+            pg[0] = pa.x; pg[1] = pa.y;
+            if (G == 4) { const double2 pb = row[2 * j + 1]; pg[G - 2] = pb.x; pg[G - 1] = pb.y; }
+            if (j == NG - 1 && b <= 6) pg[G - 1] = pc.y;
+        }
         if (act) {
             const unsigned qb = q + (Pb - Pprev);
             ok = ok && qb < (1u << 24) && (int)(pk & 0x7FFu) == ex;
             double r = grid_to_double(ex, qb);
-            r = (double)(float)(r + pa.x); // reference src/tempo_atk_sort.c:147
-            r = (double)(float)(r + pa.y);
-            r = (double)(float)(r + pb.x);
-            r = (double)(float)(r + p3);
+#pragma unroll
+            for (int i = 0; i < G; ++i) r = (double)(float)(r + pg[i]); // reference src/tempo_atk_sort.c:147
             ex = (__double2hiint(r) >> 20) & 0x7ff;
             q = (((unsigned)__double2hiint(r) & 0xFFFFFu) << 3) | ((unsigned)__double2loint(r) >> 29) | 0x800000u;
             ok = ok && (int)((pk >> 16) & 0x7FFu) == ex && ex <= 1023 + 126;
@@ -576,7 +614,7 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
 #else
                 double ud[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) ud[i] = (double)u[i];
+                for (int i = 0; i < 16; ++i) ud[i] = BLX_ENV_CVT_MAGIC ? int_to_double_exact(u[i]) : (double)u[i];
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
                     double ye = (double)fold_e_i(0) * ud[8 + o], yd = (double)fold_d_i(0) * ud[8 + o];
@@ -606,7 +644,7 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
 #if !BLX_ENV_FIR_INT
                 double xd[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) xd[i] = (double)xv[i];
+                for (int i = 0; i < 32; ++i) xd[i] = BLX_ENV_CVT_MAGIC ? int_to_double_exact(xv[i]) : (double)xv[i];
 #endif
 #pragma unroll
                 for (int o2 = 0; o2 < 8; ++o2) {
@@ -677,7 +715,9 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
         {
             const int hop = B0 + 2 * q + hw;
             const bool active = 2 * q + hw < n_mine;
+#if !defined(BLX_ENV_EXPERIMENT_NOFFT) // timing experiment only (wrong results): what the kernel costs without the FFT proper
             fft256_halfwarp<double>(v, lane16, xchg, p.tw1, full);
+#endif
             __syncwarp(full);
 #pragma unroll
             for (int r = 0; r < 16; ++r) // only Z[129..255] are read back below
@@ -722,7 +762,11 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
                 xr[pidx(128)] = 4.0 * (Zk.x * Zk.x + Zk.y * Zk.y);
             }
             __syncwarp(full);
-            const double e = float_chain(xr, lane16, active, p.slow_chain != 0);
+#if defined(BLX_ENV_EXPERIMENT_NOCHAIN) // timing experiment only (wrong results): what the kernel costs without the accumulation
+            const double e = xr[pidx(1 + lane16)] + xr[15];
+#else
+            const double e = float_chain<BLX_ENV_CHAIN_G>(xr, lane16, active, p.slow_chain != 0);
+#endif
             if (active && lane16 == 0) p.energy[sd.env_off + hop] = e;
         }
         __syncwarp(full); // the exchange buffers are free for the next pair's FIR block

@@ -6,10 +6,10 @@ set -e
 cd "$(dirname "$0")/.."
 VAR=tools/variants
 declare -A FLAGS=(
-  [int8]="-DBLX_ENV_FIR_INT=1 -DBLX_ENV_WARPS=8"
-  [fp8]="-DBLX_ENV_FIR_INT=0 -DBLX_ENV_WARPS=8"
-  [int9]="-DBLX_ENV_FIR_INT=1 -DBLX_ENV_WARPS=9"
-  [fp9]="-DBLX_ENV_FIR_INT=0 -DBLX_ENV_WARPS=9"
+  [base]=""
+  [nochain]="-DBLX_ENV_EXPERIMENT_NOCHAIN"
+  [nofft]="-DBLX_ENV_EXPERIMENT_NOFFT"
+  [neither]="-DBLX_ENV_EXPERIMENT_NOCHAIN -DBLX_ENV_EXPERIMENT_NOFFT"
 )
 if [ "$1" = build ]; then
   mkdir -p $VAR
