@@ -25,6 +25,14 @@ class BlxError(RuntimeError):
     pass
 
 
+def _c_array(ctype, values):
+    """A ctypes array of `values`; an array of the right type passes through (callers that reuse the same offsets /
+    lengths for many launches build it once)."""
+    if isinstance(values, ctypes.Array) and values._type_ is ctype:
+        return values
+    return (ctype * len(values))(*[int(v) for v in values])
+
+
 def _stream_arg(stream):
     """cudaStream_t for the C-ABI. None = the engine's own stream. A handle of 0 is CUDA's legacy default stream (what
     torch.cuda.current_stream().cuda_stream returns outside a stream context): it is passed as cudaStreamLegacy (0x1),
@@ -109,10 +117,10 @@ class Engine:
         """wait=False: blx_analyze_device_async - `stream` is not made to wait for the results; call join(stream)
         after the last batch of the job."""
         n = len(offsets)
-        offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
-        lens = (ctypes.c_int64 * n)(*[int(x) for x in lengths])
-        durs = (ctypes.c_uint64 * n)(*[int(d) for d in durations]) if durations is not None else None
-        chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
+        offs = _c_array(ctypes.c_int64, offsets)
+        lens = _c_array(ctypes.c_int64, lengths)
+        durs = _c_array(ctypes.c_uint64, durations) if durations is not None else None
+        chs = _c_array(ctypes.c_int, channels) if channels is not None else None
         f = self._lib.blx_analyze_device if wait else self._lib.blx_analyze_device_async
         self._ck(f(self._h, fmt, ctypes.c_void_p(int(d_pcm)), offs, lens, chs, durs, n, what, ctypes.c_void_p(int(d_out)),
                    _stream_arg(stream)))
@@ -123,9 +131,9 @@ class Engine:
 
     def spectral_device(self, fmt, d_pcm, offsets, lengths, d_frequency, channels=None, stream=None):
         n = len(offsets)
-        offs = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
-        lens = (ctypes.c_int64 * n)(*[int(x) for x in lengths])
-        chs = (ctypes.c_int * n)(*[int(c) for c in channels]) if channels is not None else None
+        offs = _c_array(ctypes.c_int64, offsets)
+        lens = _c_array(ctypes.c_int64, lengths)
+        chs = _c_array(ctypes.c_int, channels) if channels is not None else None
         self._ck(self._lib.blx_spectral_device(self._h, fmt, ctypes.c_void_p(int(d_pcm)), offs, lens, chs, n,
                                                ctypes.c_void_p(int(d_frequency)),
                                                _stream_arg(stream)))
