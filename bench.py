@@ -826,28 +826,60 @@ def run_ours(args):
         Be = max(8, min(Be, fit))
     except Exception:
         pass
-    pinned = torch.empty(Be * stride, dtype=torch.float32, pin_memory=True)
-    pinned.copy_(buf[:Be * stride])
+    # Ranks of one box do not see the same host link: with all GPUs copying at once, four of the eight GPUs of this pool's
+    # boxes get 23 GB/s and four 35 GB/s (alone: 55 GB/s each; tools/h2d_probe.py, profiles/r2_h2d_probe_n8.json). Every rank
+    # therefore takes a share of the step's songs in proportion to the copy rate it measures while all ranks copy, so that
+    # the ranks finish together; the total stays world x Be songs per step.
+    share = Be
+    rates = None
+    if world > 1:
+        probe = torch.empty(64 << 20, dtype=torch.float32, pin_memory=True)  # 256 MiB
+        dst = torch.empty_like(probe, device=dev)
+        dst.copy_(probe, non_blocking=True)
+        barrier()
+        ev0.record()
+        for _ in range(6):
+            dst.copy_(probe, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        mine = 6 * probe.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        tr = torch.tensor([mine], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(tr) for _ in range(world)]
+        dist.all_gather(allr, tr)
+        rates = [float(x.item()) for x in allr]
+        share = max(8, min(B, int(round(world * Be * rates[rank] / sum(rates)))))
+        del probe, dst
+        barrier()
+    Be_mine = share
+    pinned = torch.empty(Be_mine * stride, dtype=torch.float32, pin_memory=True)
+    pinned.copy_(buf[:Be_mine * stride])
     torch.cuda.synchronize()
-    ptrs = [pinned.data_ptr() + 4 * o for o in offs[:Be]]
-    out_host = np.zeros(Be, dtype=bliss_b200.RESULT_DTYPE)
+    ptrs = [pinned.data_ptr() + 4 * (i * stride) for i in range(Be_mine)]
+    lens_e = [n_in] * Be_mine
+    out_host = np.zeros(Be_mine, dtype=bliss_b200.RESULT_DTYPE)
     for _ in range(max(1, min(args.warmup, 2))):
-        eng.analyze_host_ptrs(E.FMT_F32, ptrs, lens[:Be], out=out_host)
+        eng.analyze_host_ptrs(E.FMT_F32, ptrs, lens_e, out=out_host)
     barrier()
     e2e_steps = max(1, min(args.steps, 8))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.analyze_host_ptrs(E.FMT_F32, ptrs, lens[:Be], out=out_host)  # synchronous: results are on the host
+        eng.analyze_host_ptrs(E.FMT_F32, ptrs, lens_e, out=out_host)  # synchronous: results are on the host
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    if out_host.tobytes() != res[:Be].tobytes():
+    my_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(my_s)
+    if out_host.tobytes() != res[:Be_mine].tobytes():
         for k in out_host.dtype.names:
-            d = np.flatnonzero(out_host[k] != res[:Be][k])
+            d = np.flatnonzero(out_host[k] != res[:Be_mine][k])
             if len(d):
                 log(f"  field {k}: {len(d)} songs differ, e.g. song {d[0]}: host {out_host[k][d[0]]!r} device {res[k][d[0]]!r}")
         raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
+    songs_all = Be_mine
+    if world > 1:
+        ts = torch.tensor([float(Be_mine)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        songs_all = int(ts.item())
     # raw pinned host -> device bandwidth of this box, for context: the e2e path is PCIe-bound
-    probe_n = min(Be, 64) * stride
+    probe_n = min(Be_mine, 64) * stride
     dprobe = torch.empty(probe_n, dtype=torch.float32, device=dev)
     dprobe.copy_(pinned[:probe_n], non_blocking=True)
     torch.cuda.synchronize()
@@ -858,10 +890,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     h2d_gbs = 3 * probe_n * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
     del dprobe
-    e2e = {"value": world * Be * e2e_steps / e2e_s, "unit": UNIT, "h2d_achieved_gbs": Be * e2e_steps * n_in * 4 / e2e_s / 1e9,
-           "h2d_memcpy_peak_gbs": h2d_gbs, "h2d_bytes_per_step": world * Be * n_in * 4,
-           "d2h_bytes_per_step": world * Be * 32, "songs_per_step": world * Be, "steps": e2e_steps,
-           "api": "blx_analyze_batch_f32 (include/blx.h), pinned host PCM"}
+    e2e = {"value": songs_all * e2e_steps / e2e_s, "unit": UNIT, "h2d_achieved_gbs": Be_mine * e2e_steps * n_in * 4 / my_s / 1e9,
+           "h2d_memcpy_peak_gbs": h2d_gbs, "h2d_bytes_per_step": songs_all * n_in * 4,
+           "d2h_bytes_per_step": songs_all * 32, "songs_per_step": songs_all, "steps": e2e_steps,
+           "api": "blx_analyze_batch_f32 (include/blx.h), pinned host PCM",
+           "rank_shares": None if rates is None else {"rule": "songs per rank in proportion to the host->device rate each rank measures while "
+                                                              "all ranks copy at once (the box's host links are not symmetric)",
+                                                      "concurrent_h2d_gbs_per_rank": [round(r, 1) for r in rates],
+                                                      "rank0_songs": Be_mine, "aggregate_concurrent_h2d_gbs": round(sum(rates), 1)}}
 
     # ---------------- CPU baseline + parity on a bounded sample of the same songs (rank 0, N = 1 only)
     cpu_baseline, parity = None, None

@@ -64,7 +64,7 @@ BLX_H_SYMBOLS = [
     "blx_frequency_spectrum_s16", "blx_histogram_s16", "blx_envelope_tail", "blx_envelope_energy_f32",
     "blx_profile_enable", "blx_profile_reset", "blx_profile_read", "blx_kernel_name", "blx_launch_count",
     "blx_measure_fp64_peak", "blx_multi_init", "blx_multi_shutdown", "blx_multi_device_count", "blx_multi_transport",
-    "blx_multi_engine", "blx_multi_analyze_batch_s16", "blx_multi_analyze_batch_f32", "blx_multi_set_vectors", "blx_multi_nearest",
+    "blx_multi_engine", "blx_multi_songs_taken", "blx_multi_analyze_batch_s16", "blx_multi_analyze_batch_f32", "blx_multi_set_vectors", "blx_multi_nearest",
 ]
 
 _lib = None

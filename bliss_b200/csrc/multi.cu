@@ -3,8 +3,9 @@
 // The reference's callers are C programmes (reference examples/analyze.c:15-53, README.md:80); the split of
 // BASELINE.json configs[2] / configs[4] over the GPUs of a box must therefore be reachable from C, without Python or
 // torch.distributed: blx_multi owns one engine per device and one host thread per device per call.
-//   - analysis: songs shard by contiguous blocks (device r gets [r N / G, (r + 1) N / G)); no data-path collective,
-//     every device runs the ordinary host-buffer path (blx_analyze_batch_*) on its block;
+//   - analysis: no data-path collective; the device threads take units of consecutive songs from a shared counter
+//     (a device behind a slower host link takes fewer) and run the ordinary host-buffer path (blx_analyze_batch_*)
+//     on each unit;
 //   - all-pairs distances: every device keeps the force vectors of its block resident; they are all-gathered device
 //     to device - ncclAllGather over NVLink (one communicator per device, ncclCommInitAll), or peer copies when
 //     NCCL cannot start - and every device reduces the rows of its own block against all columns
@@ -73,7 +74,8 @@ struct Dev {
     int *d_idx = nullptr;
     float *d_dist = nullptr;
     size_t cap_rows = 0, cap_all = 0;
-    int lo = 0, hi = 0; // block of the last analysed / uploaded batch
+    int lo = 0, hi = 0; // block of the resident force vectors of the last analysed / uploaded batch
+    int last_taken = 0; // songs this device analysed in the last batch (dynamic units)
 };
 } // namespace
 
@@ -81,6 +83,7 @@ struct blx_multi {
     std::vector<Dev> dev;
     bool nccl = false;
     int last_n = 0; // songs of the batch whose vectors are resident
+    int unit_songs = 128;
     char transport[64] = "single device";
 };
 
@@ -157,6 +160,9 @@ extern "C" void blx_multi_shutdown(blx_multi *m) {
 
 extern "C" int blx_multi_device_count(blx_multi *m) { return m ? (int)m->dev.size() : 0; }
 extern "C" const char *blx_multi_transport(blx_multi *m) { return m ? m->transport : ""; }
+extern "C" int blx_multi_songs_taken(blx_multi *m, int rank) {
+    return (m && rank >= 0 && rank < (int)m->dev.size()) ? m->dev[rank].last_taken : -1;
+}
 extern "C" blx_engine *blx_multi_engine(blx_multi *m, int rank) {
     return (m && rank >= 0 && rank < (int)m->dev.size()) ? m->dev[rank].eng : nullptr;
 }
@@ -166,6 +172,11 @@ namespace {
 struct Job {
     blx_multi *m;
     int rank;
+    int n_songs;
+    int unit;                 // songs per unit of work taken from the shared counter
+    int *next;                // shared: first song nobody has taken yet (guarded by *lock)
+    pthread_mutex_t *lock;
+    int taken;                // songs this device ended up analysing
     int fmt; // BLX_FMT_*
     const void *const *pcm;
     const int *n_samples;     // s16
@@ -197,20 +208,35 @@ int upload_vectors(Dev &d, const blx_result *res, int n_local, int pad) {
     return BLX_OK;
 }
 
+// Every device thread takes units of consecutive songs from a shared counter until none are left: a device behind a
+// slower host link (on the 8-GPU boxes of this pool four GPUs copy at 23 GB/s and four at 35 GB/s when all are busy,
+// profiles/r2_h2d_probe_n8.json) simply ends up with fewer songs. A record depends on its song alone, so the
+// result array is the same whichever device analysed which unit.
 void *analyze_thread(void *arg) {
     Job *j = static_cast<Job *>(arg);
     Dev &d = j->m->dev[j->rank];
-    const int n = d.hi - d.lo;
     j->rc = BLX_OK;
-    if (n > 0) {
+    j->taken = 0;
+    for (;;) {
+        pthread_mutex_lock(j->lock);
+        const int lo = *j->next;
+        const int hi = std::min(j->n_songs, lo + j->unit);
+        *j->next = hi;
+        pthread_mutex_unlock(j->lock);
+        if (lo >= hi) break;
+        const int n = hi - lo;
         if (j->fmt == BLX_FMT_S16)
-            j->rc = blx_analyze_batch_s16(d.eng, reinterpret_cast<const int16_t *const *>(j->pcm) + d.lo, j->n_samples + d.lo,
-                                          j->channels ? j->channels + d.lo : nullptr, j->duration_s ? j->duration_s + d.lo : nullptr, n,
-                                          j->what, j->out + d.lo);
+            j->rc = blx_analyze_batch_s16(d.eng, reinterpret_cast<const int16_t *const *>(j->pcm) + lo, j->n_samples + lo,
+                                          j->channels ? j->channels + lo : nullptr, j->duration_s ? j->duration_s + lo : nullptr, n,
+                                          j->what, j->out + lo);
         else
-            j->rc = blx_analyze_batch_f32(d.eng, reinterpret_cast<const float *const *>(j->pcm) + d.lo, j->n_in + d.lo, n, j->what,
-                                          j->out + d.lo);
-        if (j->rc != BLX_OK) snprintf(j->err, sizeof(j->err), "device %d: %s", d.device, blx_last_error());
+            j->rc = blx_analyze_batch_f32(d.eng, reinterpret_cast<const float *const *>(j->pcm) + lo, j->n_in + lo, n, j->what,
+                                          j->out + lo);
+        if (j->rc != BLX_OK) {
+            snprintf(j->err, sizeof(j->err), "device %d: %s", d.device, blx_last_error());
+            break;
+        }
+        j->taken += n;
     }
     return nullptr;
 }
@@ -222,10 +248,19 @@ int analyze_sharded(blx_multi *m, Job proto, int n_songs) {
     const int G = (int)m->dev.size();
     std::vector<Job> jobs(G, proto);
     std::vector<pthread_t> th(G);
+    // units of work: large enough for the engine to overlap the copy of one staging chunk with the kernels of the
+    // previous one inside a unit, small enough that the devices finish together
+    int next = 0;
+    pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
+    const int unit = std::max(1, std::min(m->unit_songs, (n_songs + 4 * G - 1) / (4 * G)));
     for (int r = 0; r < G; ++r) {
-        shard(n_songs, r, G, &m->dev[r].lo, &m->dev[r].hi);
+        shard(n_songs, r, G, &m->dev[r].lo, &m->dev[r].hi); // blocks of the resident force vectors (blx_multi_nearest)
         jobs[r].m = m;
         jobs[r].rank = r;
+        jobs[r].n_songs = n_songs;
+        jobs[r].unit = unit;
+        jobs[r].next = &next;
+        jobs[r].lock = &lock;
         jobs[r].err[0] = 0;
         if (pthread_create(&th[r], nullptr, analyze_thread, &jobs[r]) != 0) {
             for (int s = 0; s < r; ++s) pthread_join(th[s], nullptr);
@@ -233,8 +268,10 @@ int analyze_sharded(blx_multi *m, Job proto, int n_songs) {
         }
     }
     for (int r = 0; r < G; ++r) pthread_join(th[r], nullptr);
-    for (int r = 0; r < G; ++r)
+    for (int r = 0; r < G; ++r) {
+        m->dev[r].last_taken = jobs[r].taken;
         if (jobs[r].rc != BLX_OK) return blx_set_error(jobs[r].rc, "%s", jobs[r].err);
+    }
     // keep every block's force vectors resident on its device for blx_multi_nearest
     const int pad = (n_songs + G - 1) / G;
     for (int r = 0; r < G; ++r) {

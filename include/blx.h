@@ -151,9 +151,10 @@ int blx_cosine_nearest_device(blx_engine *e, const float *d_vectors, int n, int 
                               float *d_similarity, void *stream);
 
 /* ---- several GPUs from one C process ---------------------------------------------
- * BASELINE.json configs[2] / configs[4] without Python: one engine + one host thread per device. Songs shard in
- * contiguous blocks (device r analyses [r N / G, (r + 1) N / G)), no data-path collective; the force vectors of
- * every block stay resident on its device. blx_multi_nearest all-gathers them device to device (ncclAllGather over
+ * BASELINE.json configs[2] / configs[4] without Python: one engine + one host thread per device. The device
+ * threads take units of up to 128 consecutive songs from a shared counter (no data-path collective; a device on a
+ * slower host link ends up with fewer songs; records do not depend on which device analysed them); afterwards the
+ * force vectors stay resident in contiguous blocks (device r holds songs [r N / G, (r + 1) N / G)). blx_multi_nearest all-gathers them device to device (ncclAllGather over
  * NVLink; peer copies if NCCL cannot start - blx_multi_transport says which) and reduces every device's rows
  * against all columns: nearest other song per song, with the bl_distance semantics of blx_distance_nearest_device.
  * devices == NULL: the first n_devices visible devices (n_devices <= 0: all). */
@@ -163,6 +164,7 @@ void blx_multi_shutdown(blx_multi *m);
 int blx_multi_device_count(blx_multi *m);
 const char *blx_multi_transport(blx_multi *m);
 blx_engine *blx_multi_engine(blx_multi *m, int rank);
+int blx_multi_songs_taken(blx_multi *m, int rank); /* songs device `rank` analysed in the last batch */
 int blx_multi_analyze_batch_s16(blx_multi *m, const int16_t *const *pcm, const int *n_samples, const int *channels,
                                 const uint64_t *duration_s, int n_songs, unsigned what, blx_result *out);
 int blx_multi_analyze_batch_f32(blx_multi *m, const float *const *pcm, const int64_t *n_in, int n_songs, unsigned what,

@@ -76,6 +76,10 @@ int main(int argc, char **argv) {
     memset(got, 0xff, sizeof(got));
     CHECK(blx_multi_analyze_batch_s16(m, (const int16_t *const *)pcm, ns, ch, dur, S, BLX_DO_ALL, got) == BLX_OK, "%s", blx_last_error());
     CHECK(memcmp(ref, got, sizeof(ref)) == 0, "sharded records differ from the single-device records");
+    int taken = 0;
+    for (int r = 0; r < G; ++r) { printf("%sdevice %d took %d songs", r ? ", " : "", r, blx_multi_songs_taken(m, r)); taken += blx_multi_songs_taken(m, r); }
+    printf("\n");
+    CHECK(taken == S, "units taken: %d of %d songs", taken, S);
 
     /* the chained step: resident vectors -> all-gather -> nearest neighbour per song */
     int idx[37];
