@@ -73,7 +73,7 @@ struct Slot {
     size_t h_songs_cap = 0;
     blx_result *h_results = nullptr; // pinned
     size_t h_results_cap = 0;
-    cudaEvent_t copied = nullptr, done = nullptr, env_done = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr, env_done = nullptr, p1_done = nullptr, ep_done = nullptr;
     bool busy = false;
     int n_songs = 0;
     int first_song = 0; // index in the caller's batch
@@ -222,6 +222,8 @@ extern "C" int blx_init(int device, blx_engine **out) {
         CK(cudaEventCreateWithFlags(&e->slot[i].copied, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&e->slot[i].env_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->slot[i].p1_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->slot[i].ep_done, cudaEventDisableTiming));
     }
     if (const char *sb = getenv("BLX_SUB_BATCH")) e->sub_batch = std::max(1, atoi(sb));
     // constant tables, computed once in double on the host
@@ -268,6 +270,8 @@ extern "C" void blx_shutdown(blx_engine *e) {
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
         if (s.env_done) cudaEventDestroy(s.env_done);
+        if (s.p1_done) cudaEventDestroy(s.p1_done);
+        if (s.ep_done) cudaEventDestroy(s.ep_done);
     }
     if (e->fence) cudaEventDestroy(e->fence);
     if (e->joined_work) cudaEventDestroy(e->joined_work);
@@ -393,10 +397,13 @@ static int ensure_host_songs(Slot &s, int n) {
 // The descriptors are uploaded here unless the caller already queued that copy (host-buffer path: behind the
 // chunk's PCM on the copy stream - a small host->device copy on the compute stream would wait in the copy
 // engine behind the NEXT chunk's PCM and stall this chunk's kernels for a whole chunk copy).
-// st: pass 1, epilogue, envelope; st_tail: log compression + tail (may be the same stream). The caller records the
-// chunk's completion on st_tail (st for the spectral-only form).
-static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *d_pcm, int n, unsigned what,
-                     blx_result *d_out, float *d_freq_only, cudaStream_t st, cudaStream_t st_tail, bool songs_uploaded = false) {
+// A chunk runs in two halves so that a caller with several chunks can put the first half of chunk k + 1 in front of
+// the second half of chunk k:
+//   chunk_front: pass 1 on `st`, then the epilogue (one latency-bound CTA per song) on `st_side`;
+//   chunk_back:  envelope on `st` (behind the epilogue's event), then log compression + tail on `st_side`.
+// With st_side == st everything is one in-order sequence. The caller records the chunk's completion on st_side.
+static int chunk_front(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *d_pcm, int n, unsigned what, float *d_freq_only,
+                       cudaStream_t st, cudaStream_t st_side, bool songs_uploaded) {
     const bool full = (d_freq_only == nullptr);
     CK(s.songs.reserve((size_t)n * sizeof(SongDesc)));
     CK(s.partials.reserve((size_t)std::max(plan.parts_total, 1) * 256 * sizeof(float)));
@@ -431,6 +438,10 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         ProfScope ps(e, BLX_K_PASS1, st);
         CK(launch_pass1(plan.kind, full, p, plan.max_parts, n, st));
     }
+    if (st_side != st) {
+        CK(cudaEventRecord(s.p1_done, st));
+        CK(cudaStreamWaitEvent(st_side, s.p1_done, 0));
+    }
     {
         EpilogueParams p;
         p.songs = d_songs;
@@ -441,10 +452,17 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         p.frequency = d_freq_only;
         p.energy = (full && (what & BLX_DO_ENVELOPE)) ? static_cast<double *>(s.energy.p) : nullptr;
         p.what = full ? what : BLX_DO_FREQUENCY;
-        ProfScope ps(e, BLX_K_EPILOGUE, st);
-        CK(launch_epilogue(p, n, st));
+        ProfScope ps(e, BLX_K_EPILOGUE, st_side);
+        CK(launch_epilogue(p, n, st_side));
     }
-    if (!full) return BLX_OK;
+    if (st_side != st) CK(cudaEventRecord(s.ep_done, st_side));
+    return BLX_OK;
+}
+
+static int chunk_back(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *d_pcm, int n, unsigned what, blx_result *d_out,
+                      cudaStream_t st, cudaStream_t st_side) {
+    const SongDesc *d_songs = static_cast<const SongDesc *>(s.songs.p);
+    if (st_side != st) CK(cudaStreamWaitEvent(st, s.ep_done, 0));
     if (what & BLX_DO_ENVELOPE) {
         EnvelopeParams p;
         p.stream = (plan.kind == kInF32) ? static_cast<const short *>(s.q.p) : static_cast<const short *>(d_pcm);
@@ -458,13 +476,13 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         ProfScope ps(e, BLX_K_ENVELOPE, st);
         CK(launch_envelope(p, plan.max_hops, n, st));
     }
-    if (st_tail != st) {
+    if (st_side != st) {
         CK(cudaEventRecord(s.env_done, st));
-        CK(cudaStreamWaitEvent(st_tail, s.env_done, 0));
+        CK(cudaStreamWaitEvent(st_side, s.env_done, 0));
     }
     if (what & BLX_DO_ENVELOPE) {
-        ProfScope ps(e, BLX_K_TAIL, st_tail);
-        CK(launch_logcomp(static_cast<const double *>(s.energy.p), static_cast<double *>(s.xlog.p), plan.energy_total, st_tail));
+        ProfScope ps(e, BLX_K_TAIL, st_side);
+        CK(launch_logcomp(static_cast<const double *>(s.energy.p), static_cast<double *>(s.xlog.p), plan.energy_total, st_side));
     }
     {
         TailParams p;
@@ -473,10 +491,17 @@ static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *
         p.xlog = static_cast<const double *>(s.xlog.p);
         p.out = d_out;
         p.what = what;
-        ProfScope ps(e, BLX_K_TAIL, st_tail);
-        CK(launch_tail(p, n, st_tail));
+        ProfScope ps(e, BLX_K_TAIL, st_side);
+        CK(launch_tail(p, n, st_side));
     }
     return BLX_OK;
+}
+
+static int run_chunk(blx_engine *e, Slot &s, const ChunkPlan &plan, const void *d_pcm, int n, unsigned what,
+                     blx_result *d_out, float *d_freq_only, cudaStream_t st, cudaStream_t st_side, bool songs_uploaded = false) {
+    int rc = chunk_front(e, s, plan, d_pcm, n, what, d_freq_only, st, st_side, songs_uploaded);
+    if (rc || d_freq_only) return rc;
+    return chunk_back(e, s, plan, d_pcm, n, what, d_out, st, st_side);
 }
 
 static int check_engine(blx_engine *e) {
@@ -519,6 +544,10 @@ static int analyze_device_impl(blx_engine *e, int fmt, const void *d_pcm, const 
     // the spectral-only form has no tail: one sequence per run of songs, all on the compute stream
     const int sub = spectral ? 65535 : std::min(e->sub_batch, 65535);
     // songs are processed in runs of equal channel count
+    Slot *pend = nullptr; // sub-batch whose second half (envelope, tail) is still to be enqueued
+    ChunkPlan pend_plan;
+    int pend_n = 0;
+    blx_result *pend_out = nullptr;
     int i0 = 0;
     while (i0 < n_songs) {
         const int ch0 = (fmt == BLX_FMT_S16 && channels) ? channels[i0] : 2;
@@ -543,12 +572,30 @@ static int analyze_device_impl(blx_engine *e, int fmt, const void *d_pcm, const 
                    ch0 == 1 ? kInS16Mono : kInS16Stereo,
                    duration_s ? reinterpret_cast<const unsigned long long *>(duration_s + i0) : nullptr, n, s.h_songs, &plan,
                    spectral);
-        rc = run_chunk(e, s, plan, d_pcm, n, what, d_out ? d_out + i0 : nullptr, d_freq_only ? d_freq_only + i0 : nullptr,
-                       work, spectral ? work : e->tail);
-        if (rc) return rc;
-        CK(cudaEventRecord(s.done, spectral ? work : e->tail));
-        s.busy = true;
+        if (spectral) {
+            rc = run_chunk(e, s, plan, d_pcm, n, what, nullptr, d_freq_only + i0, work, work);
+            if (rc) return rc;
+            CK(cudaEventRecord(s.done, work));
+            s.busy = true;
+        } else {
+            // software pipeline over the sub-batches: pass 1 + epilogue of this one go in front of the envelope kernel of
+            // the previous one, so that the epilogue (side stream) runs under an envelope kernel, not between two kernels
+            rc = chunk_front(e, s, plan, d_pcm, n, what, nullptr, work, e->tail, false);
+            if (rc) return rc;
+            s.busy = true;
+            if (pend) {
+                rc = chunk_back(e, *pend, pend_plan, d_pcm, pend_n, what, pend_out, work, e->tail);
+                if (rc) return rc;
+                CK(cudaEventRecord(pend->done, e->tail));
+            }
+            pend = &s; pend_plan = plan; pend_n = n; pend_out = d_out + i0;
+        }
         i0 = i1;
+    }
+    if (pend) {
+        rc = chunk_back(e, *pend, pend_plan, d_pcm, pend_n, what, pend_out, work, e->tail);
+        if (rc) return rc;
+        CK(cudaEventRecord(pend->done, e->tail));
     }
     if (!async && !spectral) return join_stream(e, user);
     return BLX_OK;
