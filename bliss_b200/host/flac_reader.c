@@ -85,6 +85,33 @@ static inline size_t br_bytepos(const bitrd *b) { return b->pos - (size_t)(b->cn
 /* ------------------------------------------------------------------ */
 /* FLAC                                                                */
 /* ------------------------------------------------------------------ */
+/* Frame checksums (RFC 9639 section 9.1.8 / 9.3): CRC-8 of the header (polynomial x^8 + x^2 + x + 1) and CRC-16 of
+ * the whole frame (x^16 + x^15 + x^2 + 1), both MSB first with a zero start value. A sync code inside damaged or
+ * foreign data is only accepted as a frame when both match. */
+static uint8_t crc8_of(const uint8_t *p, size_t n) {
+    uint8_t c = 0;
+    for (size_t i = 0; i < n; ++i) {
+        c ^= p[i];
+        for (int k = 0; k < 8; ++k) c = (uint8_t)((c & 0x80) ? (c << 1) ^ 0x07 : (c << 1));
+    }
+    return c;
+}
+static uint16_t crc16_of(const uint8_t *p, size_t n) {
+    static uint16_t tab[256];
+    static int ready = 0;
+    if (!ready) {
+        for (int i = 0; i < 256; ++i) {
+            uint16_t c = (uint16_t)(i << 8);
+            for (int k = 0; k < 8; ++k) c = (uint16_t)((c & 0x8000) ? (c << 1) ^ 0x8005 : (c << 1));
+            tab[i] = c;
+        }
+        ready = 1;
+    }
+    uint16_t c = 0;
+    for (size_t i = 0; i < n; ++i) c = (uint16_t)((c << 8) ^ tab[(c >> 8) ^ p[i]]);
+    return c;
+}
+
 static int read_residual(bitrd *b, int32_t *out, int blocksize, int pred_order) {
     int method = (int)br_u(b, 2);
     if (method > 1) return -1;
@@ -120,12 +147,13 @@ static int read_subframe(bitrd *b, int32_t *out, int blocksize, int bps) {
     int wasted = 0;
     if (br_u(b, 1)) wasted = (int)br_unary(b) + 1;
     bps -= wasted;
-    if (bps <= 0 || bps > 33) return -1;
+    /* samples are kept in int32: the 33-bit side channel of a 32-bit stereo stream is not supported */
+    if (bps <= 0 || bps > 32) return -1;
     if (type == 0) { /* constant */
-        int32_t v = (bps > 32) ? (int32_t)(((int64_t)br_s(b, 1) << 32) | br_u(b, 32)) : br_s(b, bps);
+        int32_t v = br_s(b, bps);
         for (int i = 0; i < blocksize; ++i) out[i] = v;
     } else if (type == 1) { /* verbatim */
-        for (int i = 0; i < blocksize; ++i) out[i] = br_s(b, bps > 32 ? 32 : bps);
+        for (int i = 0; i < blocksize; ++i) out[i] = br_s(b, bps);
     } else if (type >= 8 && type <= 12) { /* fixed predictor */
         int order = type - 8;
         if (order > blocksize) return -1;
@@ -174,9 +202,11 @@ static void add_tag(blx_pcm_file *f, const char *kv, size_t len) {
     char **dst[5] = {&f->tracknumber, &f->title, &f->artist, &f->album, &f->genre};
     for (int i = 0; i < 5; ++i) {
         if (strlen(keys[i]) == klen && strncasecmp(kv, keys[i], klen) == 0 && !*dst[i]) {
-            *dst[i] = (char *)malloc(vlen + 1);
-            memcpy(*dst[i], eq + 1, vlen);
-            (*dst[i])[vlen] = '\0';
+            char *v = (char *)malloc(vlen + 1);
+            if (!v) return;
+            memcpy(v, eq + 1, vlen);
+            v[vlen] = '\0';
+            *dst[i] = v;
         }
     }
 }
@@ -254,7 +284,11 @@ static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
         else { pos++; continue; }
         if (sr_code == 12) br_u(&b, 8);
         else if (sr_code == 13 || sr_code == 14) br_u(&b, 16);
-        br_u(&b, 8); /* CRC-8 (not verified; STREAMINFO md5 is checked by the tests) */
+        {
+            const size_t hdr_end = br_bytepos(&b);
+            const uint32_t crc8 = br_u(&b, 8);
+            if (b.err || hdr_end > n || crc8 != crc8_of(d + pos, hdr_end - pos)) { pos++; continue; } /* a false sync */
+        }
         static const int ss_tab[8] = {0, 8, 12, 0, 16, 20, 24, 32};
         int bps = ss_tab[ss_code] ? ss_tab[ss_code] : f->bits_per_sample;
         int nch = (ch_code < 8) ? ch_code + 1 : 2;
@@ -267,8 +301,12 @@ static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
         }
         if (!ok) { pos++; continue; }
         br_align(&b);
-        br_u(&b, 16); /* CRC-16 */
-        if (b.err) break;
+        {
+            const size_t body_end = br_bytepos(&b);
+            const uint32_t crc16 = br_u(&b, 16);
+            if (b.err) break;
+            if (crc16 != crc16_of(d + pos, body_end - pos)) { pos++; continue; } /* damaged frame: resynchronise */
+        }
 
         int32_t *c0 = chbuf, *c1 = chbuf + 65536;
         if (ch_code == 8) { for (int i = 0; i < blocksize; ++i) c1[i] = c0[i] - c1[i]; }

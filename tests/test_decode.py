@@ -89,3 +89,34 @@ def test_files_at_other_rates_and_formats_go_through_the_resampler(tmp_path, ora
         assert s.duration == len(np.asarray(data).reshape(-1, ch)) // rate, name
         assert np.array_equal(got, want), (name, int(np.abs(got.astype(int) - want).max()))
         L.bl_free_song(ctypes.byref(s))
+
+
+def test_flac_frame_checksums_reject_damaged_frames(tmp_path):
+    """A FLAC frame whose CRC-16 (or header CRC-8) does not match is dropped, not decoded as audio, and a sync code that
+    happens to occur inside foreign bytes is not taken for a frame: the rest of the file decodes bit for bit."""
+    from conftest import GOLDEN_DIR
+    src = open(os.path.join(GOLDEN_DIR, "song.flac"), "rb").read()
+    L, s, rc = decode(os.path.join(GOLDEN_DIR, "song.flac"))
+    assert rc == 0
+    good = pcm_of(s)
+    L.bl_free_song(ctypes.byref(s))
+    bad = bytearray(src)
+    mid = len(bad) // 2
+    for k in range(40):
+        bad[mid + k] ^= 0x5A  # damage one frame's payload
+    (tmp_path / "damaged.flac").write_bytes(bytes(bad))
+    _, s2, rc2 = decode(tmp_path / "damaged.flac")
+    assert rc2 == 0
+    got = pcm_of(s2)
+    L.bl_free_song(ctypes.byref(s2))
+    lost = len(good) - len(got)
+    assert 0 < lost <= 2 * 2 * 4096  # one (at most two) blocks of 4 096 stereo frames are gone, nothing else
+    # everything in front of the damage is untouched, everything behind it follows after the gap
+    k = next(i for i in range(0, len(got), 2) if got[i] != good[i] or got[i + 1] != good[i + 1])
+    assert np.array_equal(got[:k], good[:k]) and np.array_equal(got[k:], good[k + lost:])
+    # foreign bytes with a sync pattern in front of the first frame are skipped
+    first = src.index(b"\xff\xf8", 4 + 38)
+    (tmp_path / "junk.flac").write_bytes(src[:first] + b"\xff\xf8\xc9\x18" + bytes(range(64)) + src[first:])
+    _, s3, rc3 = decode(tmp_path / "junk.flac")
+    assert rc3 == 0 and np.array_equal(pcm_of(s3), good)
+    L.bl_free_song(ctypes.byref(s3))
