@@ -57,7 +57,7 @@ BLISS_H_SYMBOLS = [
 ]
 BLX_H_SYMBOLS = [
     "blx_device_count", "blx_init", "blx_shutdown", "blx_last_error", "blx_configure", "blx_configure_sub_batch", "blx_debug_flags",
-    "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_device", "blx_analyze_device_async", "blx_join",
+    "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_batch_f32_exact", "blx_analyze_device", "blx_analyze_device_async", "blx_join",
     "blx_spectral_device",
     "blx_distance_matrix", "blx_cosine_matrix", "blx_distance_rows_device", "blx_distance_nearest_device", "blx_cosine_nearest_device",
     "blx_mean_variance_s16", "blx_rectangular_filter", "blx_frontend_f32", "blx_resample_to_s16", "blx_envelope_energy_s16",
@@ -99,6 +99,9 @@ def load():
     L.blx_analyze_batch_f32.restype = ctypes.c_int
     L.blx_analyze_batch_f32.argtypes = [vp, ctypes.POINTER(vp), c_i64p, ctypes.c_int, ctypes.c_uint,
                                         ctypes.POINTER(BlxResult)]
+    L.blx_analyze_batch_f32_exact.restype = ctypes.c_int
+    L.blx_analyze_batch_f32_exact.argtypes = [vp, ctypes.POINTER(vp), c_i64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint,
+                                              ctypes.POINTER(BlxResult)]
     L.blx_analyze_device.restype = ctypes.c_int
     L.blx_analyze_device.argtypes = [vp, ctypes.c_int, vp, c_i64p, c_i64p, c_i32p, c_u64p, ctypes.c_int,
                                      ctypes.c_uint, vp, vp]

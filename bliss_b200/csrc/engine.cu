@@ -880,6 +880,91 @@ extern "C" int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int ki
     return BLX_OK;
 }
 
+// 44.1 kHz (or any-rate) mono / stereo float32 host buffers -> the decode-stage resampler on the device -> the native
+// int16 pipeline: what bl_analyze computes for a float file, for callers that hold the decoded float PCM themselves.
+extern "C" int blx_analyze_batch_f32_exact(blx_engine *e, const float *const *pcm, const int64_t *n_frames, int channels, int in_rate,
+                                           int n_songs, unsigned what, blx_result *out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (n_songs <= 0) return BLX_OK;
+    if (!pcm || !n_frames || !out || (channels != 1 && channels != 2)) return fail(BLX_ERR_ARG, "bad arguments");
+    if (!(what & BLX_DO_ALL)) return fail(BLX_ERR_ARG, "empty analyser mask");
+    ResampleParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.kind = BLX_RS_KIND_F32; rp.bits = 32; rp.channels = channels;
+    std::vector<float> bank;
+    blx_rs_plan plan;
+    const bool same_rate = in_rate == BLX_RS_OUT_RATE;
+    if (!same_rate) {
+        if (blx_rs_plan_make(in_rate, BLX_RS_OUT_RATE, &plan))
+            return fail(BLX_ERR_ARG, "sample rate %d Hz needs more than %d filter phases", in_rate, BLX_RS_MAX_PHASES);
+        rp.L = plan.L; rp.P = plan.P; rp.q = plan.q; rp.center = plan.center;
+        rp.mono_gain_last = BLX_RS_MONO_GAIN_LAST(in_rate) ? 1 : 0;
+        bank.resize((size_t)plan.P * plan.L);
+        blx_rs_build_f32(&plan, bank.data());
+    }
+    DevBuf d_in, d_s16, d_bank, d_res;
+    auto cleanup = [&]() { d_in.release(); d_s16.release(); d_bank.release(); d_res.release(); };
+    cudaStream_t st = e->compute;
+    if (!bank.empty()) {
+        CK(d_bank.reserve(bank.size() * 4));
+        CK(cudaMemcpyAsync(d_bank.p, bank.data(), bank.size() * 4, cudaMemcpyHostToDevice, st));
+    }
+    const size_t cap_in = e->chunk_bytes / 4; // floats of input per group of songs
+    std::vector<int64_t> offs, lens;
+    std::vector<uint64_t> durs;
+    std::vector<int64_t> in_off;
+    int i0 = 0;
+    while (i0 < n_songs) {
+        // group: consecutive songs whose input fits the staging size (a single larger song forms its own group)
+        offs.clear(); lens.clear(); durs.clear(); in_off.clear();
+        size_t used_in = 0, used_out = 0;
+        int i1 = i0;
+        while (i1 < n_songs && i1 - i0 < 65535) {
+            if (!pcm[i1] || n_frames[i1] <= 0 || n_frames[i1] > 0x3fffffffll) { cleanup(); return fail(BLX_ERR_ARG, "song %d: bad buffer", i1); }
+            const size_t need = (size_t)n_frames[i1] * channels;
+            if (i1 > i0 && used_in + need > cap_in) break;
+            const long long n_out = same_rate ? n_frames[i1] : blx_rs_out_frames(&plan, n_frames[i1], nullptr);
+            in_off.push_back((int64_t)used_in);
+            offs.push_back((int64_t)used_out);
+            lens.push_back(2 * n_out);
+            durs.push_back((uint64_t)(n_frames[i1] / in_rate)); // whole seconds of the source (reference src/decode.c:235)
+            used_in += need;
+            used_out += (size_t)round_up(std::max(2 * n_out, 1ll), BLX_ALIGN_ELEMS) + BLX_ALIGN_ELEMS;
+            ++i1;
+        }
+        const int n = i1 - i0;
+        rc = [&]() -> int {
+            CK(d_in.reserve(used_in * 4));
+            CK(d_s16.reserve(used_out * 2));
+            CK(d_res.reserve((size_t)n * sizeof(blx_result)));
+            for (int i = 0; i < n; ++i)
+                CK(cudaMemcpyAsync(static_cast<float *>(d_in.p) + in_off[i], pcm[i0 + i], (size_t)n_frames[i0 + i] * channels * 4,
+                                   cudaMemcpyHostToDevice, st));
+            for (int i = 0; i < n; ++i) {
+                rp.in = static_cast<const int *>(d_in.p) + in_off[i];
+                rp.out = static_cast<short *>(d_s16.p) + offs[i];
+                rp.bank_f32 = static_cast<const float *>(d_bank.p);
+                rp.n_in = n_frames[i0 + i];
+                rp.n_out = lens[i] / 2;
+                e->launches++;
+                CK(launch_resample(rp, st));
+            }
+            return BLX_OK;
+        }();
+        if (rc) { cleanup(); return rc; }
+        rc = blx_analyze_device(e, BLX_FMT_S16, d_s16.p, offs.data(), lens.data(), nullptr, durs.data(), n, what,
+                                static_cast<blx_result *>(d_res.p), nullptr);
+        if (rc) { cleanup(); return rc; }
+        cudaError_t ce = cudaMemcpyAsync(out + i0, d_res.p, (size_t)n * sizeof(blx_result), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) { cleanup(); return fail(BLX_ERR_CUDA, "copy of the results failed: %s", cudaGetErrorString(ce)); }
+        i0 = i1;
+    }
+    cleanup();
+    return BLX_OK;
+}
+
 // Runs the full sequence on one S16 stereo song and leaves the intermediates in slot 0.
 static int one_song_s16(blx_engine *e, const int16_t *pcm, int n_samples, uint64_t duration, unsigned what, blx_result *res) {
     const int16_t *ptrs[1] = {pcm};

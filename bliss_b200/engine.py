@@ -94,6 +94,18 @@ class Engine:
                                                  out.ctypes.data_as(ctypes.POINTER(L.BlxResult))))
         return out
 
+    def analyze_f32_exact(self, songs, in_rate=44100, channels=1, what=DO_ALL):
+        """float32 songs through the decode-stage resampler (libswresample-exact) + the native int16 analysis:
+        what bl_analyze gives for a float file of that rate."""
+        n = len(songs)
+        songs = [np.ascontiguousarray(s, dtype=np.float32) for s in songs]
+        ptrs = (ctypes.c_void_p * n)(*[s.ctypes.data for s in songs])
+        lens = (ctypes.c_int64 * n)(*[len(s) // channels for s in songs])
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        self._ck(self._lib.blx_analyze_batch_f32_exact(self._h, ptrs, lens, int(channels), int(in_rate), n, what,
+                                                       out.ctypes.data_as(ctypes.POINTER(L.BlxResult))))
+        return out
+
     def analyze_host_ptrs(self, fmt, ptrs, lens, durations=None, channels=None, what=DO_ALL, out=None):
         """Like analyze_s16 / analyze_f32 on raw host addresses (e.g. pinned torch tensors)."""
         n = len(ptrs)

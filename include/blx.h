@@ -96,6 +96,13 @@ int blx_analyze_batch_s16(blx_engine *e, const int16_t *const *pcm, const int *n
 int blx_analyze_batch_f32(blx_engine *e, const float *const *pcm, const int64_t *n_in, int n_songs,
                           unsigned what, blx_result *out);
 
+/* Float32 songs (mono or stereo interleaved, any sample rate the resampler takes) exactly as bl_analyze would treat a
+ * float file: the decode-stage resampler of include/blx_resample.h on the device (FFmpeg's libswresample, bit for
+ * bit), then the native int16 analysis; duration is n_frames / in_rate whole seconds. For callers that need the
+ * reference's stream rather than the engine's own, cheaper 44.1 kHz front-end (blx_analyze_batch_f32). */
+int blx_analyze_batch_f32_exact(blx_engine *e, const float *const *pcm, const int64_t *n_frames, int channels, int in_rate,
+                                int n_songs, unsigned what, blx_result *out);
+
 /* ---- per-song analysis, DEVICE-resident packed buffer -------------------------
  * d_pcm: device pointer (BLX_FMT_S16: int16_t*, BLX_FMT_F32: float*). offsets/lengths
  * are HOST arrays in elements; channels (S16 only, NULL => 2) and duration_s (S16 only;

@@ -691,3 +691,20 @@ def test_cosine_nearest_matches_cosine_matrix(engine, oracle):
     from bliss_b200 import compat as bliss
     order, vals = bliss.playlist(engine, v, 2000, k=6, metric="cosine")
     assert set(order[:4].tolist()) == {100, 300, 301, 2000} and np.all(vals[:4] >= np.float32(0.9999999))
+
+
+def test_f32_exact_path_equals_resampler_plus_native_analysis(engine, oracle):
+    """blx_analyze_batch_f32_exact: float32 songs through the libswresample-exact resampler on the device, then the native
+    int16 pipeline - byte-identical to analysing the oracle-resampled PCM, for mono 44.1 kHz, stereo 48 kHz and a ragged batch."""
+    mono = [song_f32(900 + i, s) for i, s in enumerate([3.0, 7.3, 2.0])]
+    got = engine.analyze_f32_exact(mono, in_rate=44100, channels=1)
+    for i, x in enumerate(mono):
+        pcm = oracle.resample_to_s16(x.view(np.int32), oracle.RS_F32, 32, 1, 44100)
+        want = engine.analyze_s16([pcm], [len(x) // 44100])[0]
+        assert got[i].tobytes() == want.tobytes(), i
+        check_song(got[i], oracle.analyze(pcm, len(x) // 44100), tag=f"f32 exact mono {i}")
+    a, b = song_f32(910, 5.0, rate=48000), song_f32(911, 5.0, rate=48000)
+    st = np.stack([a, 0.7 * b], axis=1).reshape(-1).astype(np.float32)
+    got2 = engine.analyze_f32_exact([st], in_rate=48000, channels=2)[0]
+    pcm2 = oracle.resample_to_s16(st.view(np.int32), oracle.RS_F32, 32, 2, 48000)
+    assert got2.tobytes() == engine.analyze_s16([pcm2], [5])[0].tobytes()

@@ -2,6 +2,11 @@
 int16 rounding) from what the reference's decoder would hand the analysers for the same file (libswresample,
 reference src/decode.c:323-345: float/44.1 kHz -> s16/22 050 Hz/stereo)?
 
+Round 2: FILES no longer take this front-end - bl_audio_decode runs the libswresample-exact resampler of
+include/blx_resample.h (deviation 0, md5 pins reproduced), and blx_analyze_batch_f32_exact does the same for float
+buffers a caller holds. What this script measures is therefore only the default batch ABI for raw 44.1 kHz float
+streams (blx_analyze_batch_f32, the benchmark's workload), whose cheaper half-band filter is a documented choice.
+
 Runs in the build container only: drives the libswresample vendored in opencv's wheel through ctypes (see
 tools/make_golden_s32.py) and the oracle's front-end + analysers on CPU. Prints sample-level differences
 and the resulting force-vector differences for a few synthetic songs.
