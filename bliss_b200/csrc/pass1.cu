@@ -64,7 +64,7 @@ template <int KIND> struct P1Smem {
     static constexpr int off_bar = off_tw1 + 256 * 8;
     static constexpr int off_hist = off_bar + 16;
     static constexpr int bytes_lite = off_hist;
-    static constexpr int bytes_full = off_hist + kHistStride * 4;
+    static constexpr int bytes_full = off_hist + (kHistStride + 32) * 4; // + one spare counter per lane (hist_add)
 };
 
 // 2-D tensor copy global -> shared (SASS: UTMALDG), completion on an mbarrier. c0 = element, c1 = row.
@@ -82,16 +82,16 @@ __device__ __forceinline__ const float4 *swz_chunk(const unsigned char *row, uns
 __device__ __forceinline__ unsigned swz_key16(const void *row) { return ((smem_u32(row) >> 7) & 7u) << 4; }
 
 // Histogram of sample values -1904..+1902 (the only bins that can reach the integral of reference
-// src/amplitude_sort.c:69-71): one predicated shared-memory reduction per sample, on a 32-bit shared-window address
-// (the C++ form - if (bin < n) atomicAdd(&hist[bin], c) - adds a generic-to-shared address conversion, S2UR + ULEA, per
-// sample). ptxas still wraps the reduction in a branch; measured alternatives on B200: an unconditional reduction with a
-// spare counter for out-of-range samples is 20 % faster for quiet input and 6 % slower for the benchmark songs, where a
-// third of the samples fall outside the window - and louder music has more of those.
+// src/amplitude_sort.c:69-71): ONE UNCONDITIONAL shared-memory reduction per sample on a 32-bit shared-window address;
+// a sample outside the range adds to a spare counter of its lane behind the bins (never flushed). Measured on B200
+// per 1 024 benchmark songs (a third of the samples out of range): C++ `if (bin < n) atomicAdd(&hist[bin], c)` 11.1 ms
+// (divergent branch + generic-to-shared address conversion per sample), predicated `red.shared` on a shared-window
+// address 10.3 ms (ptxas still branches around it), unconditional with ONE shared spare counter 11.8 ms (same-address
+// reductions serialise), unconditional with a spare counter per lane 9.3 ms.
 __device__ __forceinline__ void hist_add(unsigned hist_s32, int v, unsigned c) {
     const unsigned bin = (unsigned)(v + 32768 - kHistLo);
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}" ::"r"(bin), "n"(kHistBins),
-                 "r"(hist_s32 + 4u * bin), "r"(c)
-                 : "memory");
+    const unsigned slot = (bin < (unsigned)kHistBins) ? bin : (unsigned)kHistStride + (threadIdx.x & 31u);
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s32 + 4u * slot), "r"(c) : "memory");
 }
 
 struct ThreadStats {

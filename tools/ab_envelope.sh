@@ -7,18 +7,19 @@ cd "$(dirname "$0")/.."
 VAR=tools/variants
 declare -A FLAGS=(
   [base]=""
-  [nochain]="-DBLX_ENV_EXPERIMENT_NOCHAIN"
-  [nofft]="-DBLX_ENV_EXPERIMENT_NOFFT"
-  [neither]="-DBLX_ENV_EXPERIMENT_NOCHAIN -DBLX_ENV_EXPERIMENT_NOFFT"
+  [hist2]="-DBLX_P1_HIST_MODE=2"
 )
 if [ "$1" = build ]; then
   mkdir -p $VAR
   make -C bliss_b200 -j8 >/dev/null
   for v in "${!FLAGS[@]}"; do
-    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC ${FLAGS[$v]} $EXTRA -Xptxas -v \
-      -c bliss_b200/csrc/envelope.cu -o $VAR/envelope_$v.o 2> $VAR/ptxas_$v.txt
-    objs=$(ls bliss_b200/csrc/*.o bliss_b200/host/*.o | grep -v csrc/envelope.o)
-    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $VAR/libbliss_$v.so $objs $VAR/envelope_$v.o -lpthread -lm
+    for src in envelope pass1; do
+      nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC ${FLAGS[$v]} $EXTRA -Xptxas -v \
+        -c bliss_b200/csrc/$src.cu -o $VAR/${src}_$v.o 2> $VAR/ptxas_${src}_$v.txt
+    done
+    cp $VAR/ptxas_envelope_$v.txt $VAR/ptxas_$v.txt
+    objs=$(ls bliss_b200/csrc/*.o bliss_b200/host/*.o | grep -v -e csrc/envelope.o -e csrc/pass1.o)
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $VAR/libbliss_$v.so $objs $VAR/envelope_$v.o $VAR/pass1_$v.o -ldl -lpthread -lm
     echo "$v: $(grep -A1 'envelope_kernelILb1' $VAR/ptxas_$v.txt | grep -o 'bytes spill stores' | head -1) $(grep -A2 'envelope_kernelILb1' $VAR/ptxas_$v.txt | grep -o 'Used [0-9]* registers' | head -1)"
   done
 else
