@@ -251,7 +251,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 (CPU)", "data": "synthetic",
-        "config": workload_config(args, S, 1),
+        # the SAME config as our arm (the workload being compared); each step here is a bounded sample of it (cpu_baseline.sample)
+        "config": workload_config(args, args.songs_per_step, args.gpus),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["workers"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -599,7 +600,7 @@ def run_ours(args):
         eng.analyze_device(E.FMT_F32, buf.data_ptr(), offs, lens, d_out.data_ptr(), stream=stream, wait=False)
 
     # ---------------- device-resident steps: `value`
-    eng.profile(not os.environ.get("BLX_BENCH_NOPROF"))  # (experiment switch: what do the per-kernel events cost?)
+    eng.profile(True)
     for _ in range(args.warmup):
         step()
     eng.join(stream)
