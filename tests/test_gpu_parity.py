@@ -708,3 +708,19 @@ def test_f32_exact_path_equals_resampler_plus_native_analysis(engine, oracle):
     got2 = engine.analyze_f32_exact([st], in_rate=48000, channels=2)[0]
     pcm2 = oracle.resample_to_s16(st.view(np.int32), oracle.RS_F32, 32, 2, 48000)
     assert got2.tobytes() == engine.analyze_s16([pcm2], [5])[0].tobytes()
+
+
+def test_twenty_minute_song(engine, oracle):
+    """Maximum sizes: a 20-minute native int16 stereo song (52.9 M samples, 206 k envelope hops, 404 envelope CTAs, 101 pass-1
+    parts) against the oracle - onset count exact, the amplitude histogram beyond 2^24 counts per bin where the reference's float
+    counters stop (reference src/amplitude_sort.c:33-39) - and the same song after a 44.1 kHz float round trip through the
+    exact resampler path."""
+    base = song_s16(123, 60.0, decorrelate=True, gain=0.08)  # quiet: the central histogram bins get far more than 2^24 hits
+    pcm = np.tile(base, 20)
+    pcm[1::7] //= 3
+    res = engine.analyze_s16([pcm], [1200])[0]
+    ref = oracle.analyze(pcm, 1200)
+    check_song(res, ref, tag="20 min")
+    assert float(res["amplitude"]) == ref["amplitude"]
+    E, Eo = engine.envelope_energy(pcm), oracle.envelope_energy(pcm)
+    assert E.shape == Eo.shape and np.array_equal(E, Eo)
