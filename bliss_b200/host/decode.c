@@ -54,9 +54,14 @@ int bl_audio_decode(char const *const filename, struct bl_song *const song) {
          * channels reads 2, exactly as reference src/decode.c:187-193 leaves it) */
         const size_t n = f.n_frames * (size_t)f.channels;
         const int shift = 16 - f.bits_per_sample;
-        int16_t *pcm = (int16_t *)malloc(n * sizeof(int16_t));
-        if (pcm) {
+        int16_t *pcm = NULL;
+        if (f.samples16) { /* 16-bit WAVE: the reader's buffer is the song's */
+            pcm = f.samples16;
+            f.samples16 = NULL;
+        } else if ((pcm = (int16_t *)malloc((n ? n : 1) * sizeof(int16_t))) != NULL) {
             for (size_t i = 0; i < n; ++i) pcm[i] = (int16_t)((uint32_t)f.samples[i] << shift);
+        }
+        if (pcm) {
             song->sample_array = (int8_t *)pcm;
             song->nSamples = (int)n;
             rc = BL_OK;
@@ -65,7 +70,7 @@ int bl_audio_decode(char const *const filename, struct bl_song *const song) {
         /* everything else goes through the resampler (reference src/decode.c:313-345: libswresample to
          * int16 / 22 050 Hz / stereo; here include/blx_resample.h on the GPU) */
         const int kind = f.is_float ? BLX_RS_KIND_F32 : is_u8 ? BLX_RS_KIND_U8 : is_s16 ? BLX_RS_KIND_S16 : BLX_RS_KIND_S32;
-        blx_engine *e = bl_engine_acquire();
+        blx_engine *e = blx_pcm_file_samples32(&f) == 0 ? bl_engine_acquire() : NULL;
         if (e) {
             int64_t n_out = 0;
             int brc = blx_resample_to_s16(e, f.samples, kind, f.bits_per_sample, f.channels, (int64_t)f.n_frames, f.sample_rate,

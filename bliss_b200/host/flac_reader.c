@@ -366,6 +366,14 @@ static int decode_wav(const uint8_t *d, size_t n, blx_pcm_file *f) {
             f->is_float = (fmt_tag == 3);
             f->container = 1;
             if (f->is_float && bytes != 4) return -1;
+            if (bytes == 2 && !f->is_float) { /* the common case: one copy, no widening (a little-endian host is assumed throughout) */
+                int16_t *p16 = (int16_t *)malloc((total ? total : 1) * sizeof(int16_t));
+                if (!p16) return -1;
+                memcpy(p16, body, nframes * (size_t)f->channels * sizeof(int16_t));
+                f->samples16 = p16;
+                f->n_frames = nframes;
+                return nframes ? 0 : -1;
+            }
             int32_t *pcm = (int32_t *)malloc((total ? total : 1) * sizeof(int32_t));
             if (!pcm) return -1;
             for (size_t i = 0; i < nframes * (size_t)f->channels; ++i) {
@@ -387,6 +395,17 @@ static int decode_wav(const uint8_t *d, size_t n, blx_pcm_file *f) {
 }
 
 /* ------------------------------------------------------------------ */
+int blx_pcm_file_samples32(blx_pcm_file *f) {
+    if (f->samples) return 0;
+    if (!f->samples16) return -1;
+    const size_t n = f->n_frames * (size_t)f->channels;
+    int32_t *pcm = (int32_t *)malloc((n ? n : 1) * sizeof(int32_t));
+    if (!pcm) return -1;
+    for (size_t i = 0; i < n; ++i) pcm[i] = f->samples16[i];
+    f->samples = pcm;
+    return 0;
+}
+
 int blx_pcm_file_read(const char *filename, blx_pcm_file *f) {
     memset(f, 0, sizeof(*f));
     FILE *fp = fopen(filename, "rb");
@@ -412,6 +431,7 @@ int blx_pcm_file_read(const char *filename, blx_pcm_file *f) {
 
 void blx_pcm_file_free(blx_pcm_file *f) {
     free(f->samples);
+    free(f->samples16);
     free(f->artist); free(f->title); free(f->album); free(f->tracknumber); free(f->genre);
     memset(f, 0, sizeof(*f));
 }

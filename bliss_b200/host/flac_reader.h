@@ -5,7 +5,8 @@
 #include <stdint.h>
 
 typedef struct blx_pcm_file {
-    int32_t *samples;      /* interleaved, n_frames * channels; raw IEEE bits when is_float */
+    int32_t *samples;      /* interleaved, n_frames * channels; raw IEEE bits when is_float; NULL while only samples16 is held */
+    int16_t *samples16;    /* 16-bit PCM WAVE files are read straight into int16 (no widening pass); else NULL */
     size_t n_frames;       /* sample frames (per channel) */
     int channels;
     int sample_rate;
@@ -18,5 +19,6 @@ typedef struct blx_pcm_file {
 } blx_pcm_file;
 
 int blx_pcm_file_read(const char *filename, blx_pcm_file *out); /* 0 on success */
+int blx_pcm_file_samples32(blx_pcm_file *f); /* makes f->samples valid (widens samples16 if need be); 0 on success */
 void blx_pcm_file_free(blx_pcm_file *f);
 #endif

@@ -16,13 +16,14 @@ so = os.path.join(tempfile.mkdtemp(), "libflacrd.so")
 subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(REPO, "bliss_b200/host/flac_reader.c")], check=True)
 rd = ctypes.CDLL(so)
 class PcmFile(ctypes.Structure):
-    _fields_ = [("samples", ctypes.POINTER(ctypes.c_int32)), ("n_frames", ctypes.c_size_t), ("channels", ctypes.c_int),
+    _fields_ = [("samples", ctypes.POINTER(ctypes.c_int32)), ("samples16", ctypes.POINTER(ctypes.c_int16)), ("n_frames", ctypes.c_size_t), ("channels", ctypes.c_int),
                 ("sample_rate", ctypes.c_int), ("bits_per_sample", ctypes.c_int), ("is_float", ctypes.c_int), ("container", ctypes.c_int),
                 ("file_bytes", ctypes.c_uint64), ("md5", ctypes.c_uint8 * 16)] + [(k, ctypes.c_char_p) for k in ("artist", "title", "album", "tracknumber", "genre")]
 rd.blx_pcm_file_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(PcmFile)]
 def read(path):
     f = PcmFile()
     assert rd.blx_pcm_file_read(path.encode(), ctypes.byref(f)) == 0
+    assert rd.blx_pcm_file_samples32(ctypes.byref(f)) == 0
     a = np.ctypeslib.as_array(f.samples, (f.n_frames * f.channels,)).copy()
     return a, f.n_frames, f.channels, f.sample_rate, f.bits_per_sample
 for name in ("libdrm", "libcrypto", "libssl"):
