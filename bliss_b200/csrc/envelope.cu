@@ -70,6 +70,11 @@ namespace blx {
 #define BLX_ENV_FIR_INT 0
 #endif
 
+#ifndef BLX_ENV_TW_SMEM
+// 1: both twiddle tables (6 KB) are copied to shared memory by every CTA; 0: read through L1 (LDG)
+#define BLX_ENV_TW_SMEM 1
+#endif
+
 namespace {
 constexpr int kPairsPerWarp = 32;                // a warp owns 64 consecutive hops
 constexpr int kSlotBytes = kHop * 8;             // one block of 256 FIR outputs (128 cells of 16 bytes)
@@ -95,7 +100,9 @@ template <bool DUP> struct EG {
     static constexpr int w_bytes = (w_bar + 16 + 127) / 128 * 128;
     static constexpr int off_tabi = warps * w_bytes;              // int[16][taps] head table (integer taps)
     static constexpr int off_tabd = off_tabi + 16 * taps * 4;         // double[16]: sum of the dropped taps
-    static constexpr int bytes = off_tabd + 16 * 8;
+    static constexpr int off_tw1 = off_tabd + 16 * 8;                 // double2[256], double2[128] (BLX_ENV_TW_SMEM)
+    static constexpr int off_tw2 = off_tw1 + 256 * 16;
+    static constexpr int bytes = BLX_ENV_TW_SMEM ? off_tw2 + 128 * 16 : off_tw1;
     static_assert(bytes <= 115712, "two CTAs per SM");
 };
 
@@ -509,6 +516,16 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
         }
         tabd[tid] = dsum;
     }
+#if BLX_ENV_TW_SMEM
+    {
+        double2 *t1 = reinterpret_cast<double2 *>(smem + G::off_tw1);
+        for (int i = tid; i < 256 + 128; i += G::threads) t1[i] = i < 256 ? p.tw1[i] : p.tw2[i - 256];
+    }
+    const double2 *tw1 = reinterpret_cast<const double2 *>(smem + G::off_tw1);
+    const double2 *tw2 = reinterpret_cast<const double2 *>(smem + G::off_tw2);
+#else
+    const double2 *tw1 = p.tw1, *tw2 = p.tw2;
+#endif
 
     unsigned char *wsm = smem + warp * G::w_bytes;
     double2 *xchg = reinterpret_cast<double2 *>(wsm + G::w_xchg) + hw * kXchgElems;
@@ -716,7 +733,7 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
             const int hop = B0 + 2 * q + hw;
             const bool active = 2 * q + hw < n_mine;
 #if !defined(BLX_ENV_EXPERIMENT_NOFFT) // timing experiment only (wrong results): what the kernel costs without the FFT proper
-            fft256_halfwarp<double>(v, lane16, xchg, p.tw1, full);
+            fft256_halfwarp<double>(v, lane16, xchg, tw1, full);
 #endif
             __syncwarp(full);
 #pragma unroll
@@ -740,7 +757,7 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
                     pa = 4.0 * (x0 * x0);
                     pb = 4.0 * (xn * xn);
                 } else {
-                    const double2 wk = p.tw2[k];
+                    const double2 wk = tw2[k];
                     const double sr = Zk.x + Bz[d].x, si = Zk.y - Bz[d].y;
                     const double dr = Zk.x - Bz[d].x, di = Zk.y + Bz[d].y;
                     const double tr = dr * wk.x - di * wk.y;

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 VAR=tools/variants
 declare -A FLAGS=(
   [base]=""
-  [hist2]="-DBLX_P1_HIST_MODE=2"
+  [twldg]="-DBLX_ENV_TW_SMEM=0"
 )
 if [ "$1" = build ]; then
   mkdir -p $VAR
