@@ -75,6 +75,25 @@ namespace blx {
 #define BLX_ENV_TW_SMEM 1
 #endif
 
+#ifndef BLX_ENV_TW_LOAD
+// 1: the twiddles between the two FFT passes are applied behind the transpose (fft16.cuh, TW_ON_LOAD)
+#define BLX_ENV_TW_LOAD 0
+#endif
+#ifndef BLX_ENV_TW2_FACTOR
+// 1: W512^(l + 16 d) = W512^l * W32^d with W32^d as immediates: one table read per pair instead of eight, four more
+// FP64 instructions per bin pair
+#define BLX_ENV_TW2_FACTOR 0
+#endif
+#ifndef BLX_ENV_DIRTY_LANE0
+// 1: the dirty groups of the accumulation are read by lane 0 of each half-warp only (two wavefronts per 128-bit read
+// instead of four); the other lanes run the same instructions on zeros and their result is not used
+#define BLX_ENV_DIRTY_LANE0 0
+#endif
+#ifndef BLX_ENV_PARTNER_SHFL
+// 1: Z[256 - k] comes from its lane by shuffles (32 wavefronts) instead of through the exchange buffer (64)
+#define BLX_ENV_PARTNER_SHFL 0
+#endif
+
 namespace {
 constexpr int kPairsPerWarp = 32;                // a warp owns 64 consecutive hops
 constexpr int kSlotBytes = kHop * 8;             // one block of 256 FIR outputs (128 cells of 16 bytes)
@@ -447,15 +466,22 @@ __device__ __forceinline__ double float_chain(double *xr, int lane16, bool activ
             found = found || take;
         }
         const int b = bit / NG, j = bit % NG;
-        const uint2 rec = *reinterpret_cast<const uint2 *>(xr + kAuxOff + kAuxLaneStride * b + j);
+        const bool reader = !BLX_ENV_DIRTY_LANE0 || lane16 == 0;
+        uint2 rec = make_uint2(0u, 0u);
+        if (reader) rec = *reinterpret_cast<const uint2 *>(xr + kAuxOff + kAuxLaneStride * b + j);
         const unsigned Pb = rec.x, pk = rec.y;
         // the group's bins (row b, elements G j .. G j + G - 1)
         const double2 *row = reinterpret_cast<const double2 *>(xr + kPRow * b);
         double pg[G];
         {
-            const double2 pa = row[(G / 2) * j], pc = row[8];
+            double2 pa = make_double2(0.0, 0.0), pb = pa, pc = pa;
+            if (reader) {
+                pa = row[(G / 2) * j];
+                pc = row[8];
+                if (G == 4) pb = row[2 * j + 1];
+            }
             pg[0] = pa.x; pg[1] = pa.y;
-            if (G == 4) { const double2 pb = row[2 * j + 1]; pg[G - 2] = pb.x; pg[G - 1] = pb.y; }
+            if (G == 4) { pg[G - 2] = pb.x; pg[G - 1] = pb.y; }
             if (j == NG - 1 && b <= 6) pg[G - 1] = pc.y;
         }
         if (act) {
@@ -474,6 +500,7 @@ __device__ __forceinline__ double float_chain(double *xr, int lane16, bool activ
     ok = ok && (!active || (qf < (1u << 24) && e_end == ex && ex <= 1023 + 126));
     double r = grid_to_double(ex, qf);
     if (rest_zero) { r = r16; ok = true; }
+    if (BLX_ENV_DIRTY_LANE0 && lane16 != 0) ok = true; // only lane 0 of a half-warp followed the dirty groups
     if (__any_sync(full, !ok) || force_slow) r = float_chain_rounds(xr, lane16, active, r16);
     return r;
 }
@@ -733,20 +760,37 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
             const int hop = B0 + 2 * q + hw;
             const bool active = 2 * q + hw < n_mine;
 #if !defined(BLX_ENV_EXPERIMENT_NOFFT) // timing experiment only (wrong results): what the kernel costs without the FFT proper
-            fft256_halfwarp<double>(v, lane16, xchg, tw1, full);
+            fft256_halfwarp<double, BLX_ENV_TW_LOAD != 0>(v, lane16, xchg, tw1, full);
 #endif
             __syncwarp(full);
+            double2 Bz[8]; // Z[256 - k] for this lane's bins k = lane16 + 16 d
+#if BLX_ENV_PARTNER_SHFL
+            // Z[256 - k] = Z[(16 - lane16) + 16 (15 - d)] sits in lane 16 - lane16, the register of output 15 - d; lane 0's
+            // partners Z[16 (16 - d)] are its own (d = 0: the bin is real, no partner)
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const double2 src = v[fft16_reg_of(15 - d)];
+                double2 t;
+                t.x = __shfl_sync(full, src.x, (16 - lane16) & 15, 16);
+                t.y = __shfl_sync(full, src.y, (16 - lane16) & 15, 16);
+                if (d > 0 && lane16 == 0) t = v[fft16_reg_of(16 - d)];
+                Bz[d] = t;
+            }
+#else
 #pragma unroll
             for (int r = 0; r < 16; ++r) // only Z[129..255] are read back below
                 if (fft16_out_index(r) >= 8) xchg[lane16 + 16 * fft16_out_index(r)] = v[r];
             __syncwarp(full);
-            double2 Bz[8]; // Z[256 - k] for this lane's bins k = lane16 + 16 d
 #pragma unroll
             for (int d = 0; d < 8; ++d) Bz[d] = xchg[(256 - (lane16 + 16 * d)) & 255];
             __syncwarp(full);
+#endif
             double *xr = reinterpret_cast<double *>(xchg); // |X_k|^2, k = 0..256, at pidx(k)
             // bins k = lane16 + 16 d and 256 - k: rows d and 15 - d (lane 0: the last element of rows d - 1 and 15 - d)
             const int ia0 = (lane16 == 0) ? -1 : lane16 - 1; // slot of bin k in row d; lane 0: see below
+#if BLX_ENV_TW2_FACTOR
+            const double2 wl = tw2[lane16];
+#endif
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 const int k = lane16 + 16 * d;
@@ -757,7 +801,22 @@ template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envel
                     pa = 4.0 * (x0 * x0);
                     pb = 4.0 * (xn * xn);
                 } else {
+#if BLX_ENV_TW2_FACTOR
+                    // W512^k = W512^lane16 * W32^d; the second factor is an immediate
+                    constexpr double kC32[8] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                                                0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                                                0.19509032201612826785};
+                    constexpr double kS32[8] = {0.0, -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474,
+                                                -0.70710678118654752440, -0.83146961230254523708, -0.92387953251128675613,
+                                                -0.98078528040323044913};
+                    double2 wk = wl;
+                    if (d > 0) {
+                        wk.x = wl.x * kC32[d] - wl.y * kS32[d];
+                        wk.y = wl.x * kS32[d] + wl.y * kC32[d];
+                    }
+#else
                     const double2 wk = tw2[k];
+#endif
                     const double sr = Zk.x + Bz[d].x, si = Zk.y - Bz[d].y;
                     const double dr = Zk.x - Bz[d].x, di = Zk.y + Bz[d].y;
                     const double tr = dr * wk.x - di * wk.y;

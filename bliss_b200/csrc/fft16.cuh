@@ -111,21 +111,35 @@ constexpr int kXchgElems = 16 * kXchgRow; // complex elements per transform (>= 
 //   tw1: shared table, tw1[c * 16 + b] = exp(-2 pi i b c / 256)
 //   mask: the 16 lanes taking part (0x0000FFFF or 0xFFFF0000)
 // The caller must __syncwarp(mask) before reusing xchg.
-template <typename T>
+template <typename T, bool TW_ON_LOAD = false>
 __device__ __forceinline__ void fft256_halfwarp(typename cplx<T>::type (&v)[16], int lane16,
                                                 typename cplx<T>::type *xchg,
                                                 const typename cplx<T>::type *tw1, unsigned mask) {
     using C = typename cplx<T>::type;
     fft16<T>(v);
+    // The twiddle W256^(b c) between the passes is applied by the lane that WRITES element (c, b) (it holds all 16
+    // outputs, so the table reads compete with 64 live registers) or, TW_ON_LOAD, by the lane that READS it (the table is
+    // symmetric in b and c; the same products, the registers are free at that point so all reads are in flight at once).
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int c = fft16_out_index(r);
-        C u = (c == 0) ? v[r] : cmul<C>(v[r], tw1[c * 16 + lane16]);
+        C u = (c == 0 || TW_ON_LOAD) ? v[r] : cmul<C>(v[r], tw1[c * 16 + lane16]);
         xchg[c * kXchgRow + lane16] = u;
     }
     __syncwarp(mask);
+    if (TW_ON_LOAD) {
+        C w[16];
 #pragma unroll
-    for (int b = 0; b < 16; ++b) v[b] = xchg[lane16 * kXchgRow + b];
+        for (int b = 0; b < 16; ++b) {
+            v[b] = xchg[lane16 * kXchgRow + b];
+            if (b > 0) w[b] = tw1[b * 16 + lane16];
+        }
+#pragma unroll
+        for (int b = 1; b < 16; ++b) v[b] = cmul<C>(v[b], w[b]);
+    } else {
+#pragma unroll
+        for (int b = 0; b < 16; ++b) v[b] = xchg[lane16 * kXchgRow + b];
+    }
     fft16<T>(v);
 }
 

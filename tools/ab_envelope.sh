@@ -7,7 +7,8 @@ cd "$(dirname "$0")/.."
 VAR=tools/variants
 declare -A FLAGS=(
   [base]=""
-  [twldg]="-DBLX_ENV_TW_SMEM=0"
+  [twload]="-DBLX_ENV_TW_LOAD=1"
+  [twload_pshfl]="-DBLX_ENV_TW_LOAD=1 -DBLX_ENV_PARTNER_SHFL=1"
 )
 if [ "$1" = build ]; then
   mkdir -p $VAR
