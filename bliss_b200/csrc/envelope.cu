@@ -49,6 +49,8 @@
 // The result equals the reference's chain except when s + p_k lies within 2^-29 grid units of a
 // rounding midpoint (the reference rounds to double, then to float; exact ties follow the parity of
 // the magic constant instead of q).
+#include <cstdio>
+#include <cstdlib>
 #include "blx_common.cuh"
 #include "fft16.cuh"
 #include "kernels.h"
@@ -75,6 +77,9 @@ namespace blx {
 #define BLX_ENV_TW_SMEM 1
 #endif
 
+#ifndef BLX_ENV_MINB
+#define BLX_ENV_MINB 2 // CTAs per SM the register allocation is sized for (__launch_bounds__)
+#endif
 #ifndef BLX_ENV_TW_LOAD
 // 1: the twiddles between the two FFT passes are applied behind the transpose (fft16.cuh, TW_ON_LOAD)
 #define BLX_ENV_TW_LOAD 0
@@ -507,7 +512,12 @@ __device__ __forceinline__ double float_chain(double *xr, int lane16, bool activ
 
 } // namespace
 
-template <bool DUP> __global__ void __launch_bounds__(EG<DUP>::threads, 2) envelope_kernel(EnvelopeParams p) {
+#ifdef BLX_ENV_MAXNREG // A/B only: an explicit register cap instead of the one __launch_bounds__ derives
+#define BLX_ENV_BOUNDS __maxnreg__(BLX_ENV_MAXNREG)
+#else
+#define BLX_ENV_BOUNDS __launch_bounds__(EG<DUP>::threads, BLX_ENV_MINB)
+#endif
+template <bool DUP> __global__ void BLX_ENV_BOUNDS envelope_kernel(EnvelopeParams p) {
     using G = EG<DUP>;
     extern __shared__ __align__(128) unsigned char smem[];
     const SongDesc sd = p.songs[blockIdx.y];
@@ -854,7 +864,15 @@ cudaError_t launch_envelope(const EnvelopeParams &p, int max_hops, int n_songs, 
     const cudaError_t e0 = once.run([] {
         cudaError_t e = cudaFuncSetAttribute(envelope_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<true>::bytes);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(envelope_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<false>::bytes);
+        e = cudaFuncSetAttribute(envelope_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EG<false>::bytes);
+        if (e == cudaSuccess && getenv("BLX_DEBUG_OCCUPANCY")) {
+            int a = 0, b = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, envelope_kernel<true>, EG<true>::threads, EG<true>::bytes);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, envelope_kernel<false>, EG<false>::threads, EG<false>::bytes);
+            fprintf(stderr, "envelope_kernel: %d CTAs/SM of %d threads, %d B (doubled mono); %d of %d threads, %d B (stereo)\n", a,
+                    EG<true>::threads, EG<true>::bytes, b, EG<false>::threads, EG<false>::bytes);
+        }
+        return e;
     });
     if (e0 != cudaSuccess) return e0;
     if (max_hops <= 0) return cudaSuccess;

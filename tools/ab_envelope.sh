@@ -7,8 +7,7 @@ cd "$(dirname "$0")/.."
 VAR=tools/variants
 declare -A FLAGS=(
   [base]=""
-  [twload]="-DBLX_ENV_TW_LOAD=1"
-  [twload_pshfl]="-DBLX_ENV_TW_LOAD=1 -DBLX_ENV_PARTNER_SHFL=1"
+  [pshfl]="-DBLX_ENV_PARTNER_SHFL=1"
 )
 if [ "$1" = build ]; then
   mkdir -p $VAR
@@ -27,8 +26,9 @@ else
   songs=${2:-1024}
   for so in $VAR/libbliss_*.so; do
     v=$(basename $so .so)
-    BLISS_B200_LIB=$PWD/$so python bench.py --steps 3 --warmup 2 --songs-per-step $songs --no-cpu --no-spectral --no-distance \
+    BLX_DEBUG_OCCUPANCY=1 BLISS_B200_LIB=$PWD/$so python bench.py --steps 3 --warmup 2 --songs-per-step $songs --no-cpu --no-spectral --no-distance \
       --e2e-songs 2 --s16-songs 128 --parity-songs 0 --chain-songs 0 --no-bl-analyze > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || echo "$v FAILED"
+    grep -h "CTAs/SM" gpurun_out/ab_$v.err | head -1
     python - "$v" gpurun_out/ab_$v.json <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
