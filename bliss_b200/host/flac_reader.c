@@ -406,6 +406,49 @@ int blx_pcm_file_samples32(blx_pcm_file *f) {
     return 0;
 }
 
+/* 16-bit PCM WAVE whose "data" chunk starts inside the first `nh` bytes (`head`): the samples are read from the file
+ * straight into the buffer the song will own - one copy of the 32 MB of a 3-minute song instead of three.
+ * 1 = done, 0 = not this kind of file (the caller reads it whole), -1 = error. */
+static int read_wav16_direct(FILE *fp, const uint8_t *head, size_t nh, size_t sz, blx_pcm_file *f) {
+    if (nh < 12 || memcmp(head, "RIFF", 4) || memcmp(head + 8, "WAVE", 4)) return 0;
+    size_t pos = 12;
+    int fmt_tag = 0, have_fmt = 0;
+    while (pos + 8 <= nh) {
+        const uint32_t len = le32(head + pos + 4);
+        if (!memcmp(head + pos, "fmt ", 4) && len >= 16 && pos + 8 + len <= nh) {
+            const uint8_t *body = head + pos + 8;
+            fmt_tag = le16(body);
+            f->channels = le16(body + 2);
+            f->sample_rate = (int)le32(body + 4);
+            f->bits_per_sample = le16(body + 14);
+            if (fmt_tag == 0xFFFE && len >= 26) fmt_tag = le16(body + 24);
+            have_fmt = 1;
+        } else if (!memcmp(head + pos, "data", 4)) {
+            if (!have_fmt || fmt_tag != 1 || f->bits_per_sample != 16 || f->channels < 1) return 0;
+            const size_t off = pos + 8;
+            size_t bytes = len;
+            if (off + bytes > sz) bytes = sz - off;
+            const size_t nframes = bytes / 2 / (size_t)f->channels;
+            bytes = nframes * (size_t)f->channels * 2;
+            if (!nframes) return -1;
+            int16_t *p16 = (int16_t *)malloc(bytes);
+            if (!p16) return -1;
+            const size_t in_head = off < nh ? (nh - off < bytes ? nh - off : bytes) : 0;
+            memcpy(p16, head + off, in_head);
+            if (fseek(fp, (long)(off + in_head), SEEK_SET) || fread((uint8_t *)p16 + in_head, 1, bytes - in_head, fp) != bytes - in_head) {
+                free(p16);
+                return -1;
+            }
+            f->samples16 = p16;
+            f->n_frames = nframes;
+            f->container = 1;
+            return 1;
+        }
+        pos += 8 + (size_t)len + (len & 1);
+    }
+    return 0;
+}
+
 int blx_pcm_file_read(const char *filename, blx_pcm_file *f) {
     memset(f, 0, sizeof(*f));
     FILE *fp = fopen(filename, "rb");
@@ -414,10 +457,22 @@ int blx_pcm_file_read(const char *filename, blx_pcm_file *f) {
     long sz = ftell(fp);
     fseek(fp, 0, SEEK_SET);
     if (sz < 16) { fclose(fp); return -1; }
-    uint8_t *d = (uint8_t *)malloc((size_t)sz);
-    if (!d || fread(d, 1, (size_t)sz, fp) != (size_t)sz) { free(d); fclose(fp); return -1; }
-    fclose(fp);
     f->file_bytes = (uint64_t)sz;
+    uint8_t head[4096];
+    const size_t nh = (size_t)sz < sizeof(head) ? (size_t)sz : sizeof(head);
+    if (fread(head, 1, nh, fp) != nh) { fclose(fp); return -1; }
+    const int direct = read_wav16_direct(fp, head, nh, (size_t)sz, f);
+    if (direct) {
+        fclose(fp);
+        if (direct < 0) blx_pcm_file_free(f);
+        return direct < 0 ? -1 : 0;
+    }
+    memset(f, 0, sizeof(*f));
+    f->file_bytes = (uint64_t)sz;
+    uint8_t *d = (uint8_t *)malloc((size_t)sz);
+    if (d) memcpy(d, head, nh);
+    if (!d || fread(d + nh, 1, (size_t)sz - nh, fp) != (size_t)sz - nh) { free(d); fclose(fp); return -1; }
+    fclose(fp);
     int rc = -1;
     size_t off = 0;
     if (!memcmp(d, "ID3", 3) && sz > 10) /* skip an ID3v2 tag in front of a FLAC stream */

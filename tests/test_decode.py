@@ -50,6 +50,38 @@ def test_wav_native_passthrough(tmp_path):
     assert s.sample_array is None and s.title is None
 
 
+def test_wav_chunk_layouts(tmp_path):
+    """16-bit PCM is read straight into the song's buffer (flac_reader.c: read_wav16_direct); the chunk walk in front of
+    it has to cope with what real files carry: a LIST chunk of odd length (padded) before `data`, WAVE_FORMAT_EXTENSIBLE,
+    a `data` length that overshoots the file (truncated download), a header pushed beyond the first 4 KB (whole-file path)."""
+    pcm = song_s16(7, 1.5, decorrelate=True)
+    raw = pcm.tobytes()
+    fmt16 = struct.pack("<HHIIHH", 1, 2, 22050, 22050 * 4, 4, 16)
+    fmt_ext = struct.pack("<HHIIHH", 0xFFFE, 2, 22050, 22050 * 4, 4, 16) + struct.pack("<HHI", 22, 16, 3) + struct.pack(
+        "<H", 1) + b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71"
+
+    def riff(chunks):
+        body = b"WAVE" + b"".join(k + struct.pack("<I", n if n is not None else len(d)) + d + (b"\x00" if len(d) & 1 else b"")
+                                  for k, d, n in chunks)
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+
+    cases = {
+        "list.wav": (riff([(b"fmt ", fmt16, None), (b"LIST", b"INFOISFT\x05\x00\x00\x00abcd\x00", None), (b"data", raw, None)]), len(pcm)),
+        "ext.wav": (riff([(b"fmt ", fmt_ext, None), (b"data", raw, None)]), len(pcm)),
+        "short.wav": (riff([(b"fmt ", fmt16, None), (b"data", raw[:len(raw) // 2 + 2], len(raw))]), (len(raw) // 2 + 2) // 4 * 2),
+        "late.wav": (riff([(b"fmt ", fmt16, None), (b"junk", bytes(6000), None), (b"data", raw, None)]), len(pcm)),
+    }
+    for name, (blob, n_expect) in cases.items():
+        (tmp_path / name).write_bytes(blob)
+        L, s, rc = decode(tmp_path / name)
+        assert rc == 0, name
+        got = pcm_of(s)
+        assert len(got) == n_expect and np.array_equal(got, pcm[:len(got)]), name
+        L.bl_free_song(ctypes.byref(s))
+    (tmp_path / "empty.wav").write_bytes(riff([(b"fmt ", fmt16, None), (b"data", b"", None)]))
+    assert decode(tmp_path / "empty.wav")[2] == -2
+
+
 def test_decode_error_paths(tmp_path, capfd):
     L, s, rc = decode(tmp_path / "missing.flac")
     assert rc == -2  # BL_UNEXPECTED
