@@ -68,6 +68,7 @@ struct Dev {
     blx_engine *eng = nullptr;
     ncclComm_t comm = nullptr;
     cudaStream_t st = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; // start / gathered / reduced (blx_multi_nearest)
     float *d_local = nullptr; // this device's block of force vectors, padded to `pad` rows
     float *d_all = nullptr;   // the gathered table (G * pad rows) and its compacted form (n rows)
     float *d_table = nullptr;
@@ -114,8 +115,13 @@ extern "C" int blx_multi_init(const int *devices, int n_devices, blx_multi **out
         m->dev[r].device = ids[r];
         int rc = blx_init(ids[r], &m->dev[r].eng);
         if (rc != BLX_OK) { blx_multi_shutdown(m); return rc; }
-        MCK(cudaSetDevice(ids[r]));
-        MCK(cudaStreamCreateWithFlags(&m->dev[r].st, cudaStreamNonBlocking));
+        cudaError_t ce = cudaSetDevice(ids[r]);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&m->dev[r].st, cudaStreamNonBlocking);
+        for (int k = 0; k < 3 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&m->dev[r].ev[k]);
+        if (ce != cudaSuccess) {
+            blx_multi_shutdown(m);
+            return blx_set_error(BLX_ERR_CUDA, "device %d: %s", ids[r], cudaGetErrorString(ce));
+        }
     }
     const int G = (int)ids.size();
     if (G > 1) {
@@ -152,6 +158,7 @@ extern "C" void blx_multi_shutdown(blx_multi *m) {
         cudaSetDevice(d.device);
         if (d.comm) g_nccl.CommDestroy(d.comm);
         if (d.st) { cudaStreamSynchronize(d.st); cudaStreamDestroy(d.st); }
+        for (cudaEvent_t e : d.ev) if (e) cudaEventDestroy(e);
         cudaFree(d.d_local); cudaFree(d.d_all); cudaFree(d.d_table); cudaFree(d.d_idx); cudaFree(d.d_dist);
         if (d.eng) blx_shutdown(d.eng);
     }
@@ -243,7 +250,8 @@ void *analyze_thread(void *arg) {
 
 int analyze_sharded(blx_multi *m, Job proto, int n_songs) {
     if (!m) return blx_set_error(BLX_ERR_ARG, "null blx_multi");
-    if (n_songs <= 0) { m->last_n = 0; return BLX_OK; }
+    m->last_n = 0; // nothing resident until this batch has gone through
+    if (n_songs <= 0) return BLX_OK;
     if (!proto.pcm || !proto.out) return blx_set_error(BLX_ERR_ARG, "null input array");
     const int G = (int)m->dev.size();
     std::vector<Job> jobs(G, proto);
@@ -327,11 +335,9 @@ extern "C" int blx_multi_nearest(blx_multi *m, int *nearest_index, float *neares
     if (!m || m->last_n <= 0) return blx_set_error(BLX_ERR_ARG, "no resident force vectors (analyse a batch or call blx_multi_set_vectors first)");
     if (!nearest_index && !nearest_dist) return blx_set_error(BLX_ERR_ARG, "no output requested");
     const int G = (int)m->dev.size(), n = m->last_n, pad = (n + G - 1) / G;
-    std::vector<cudaEvent_t> ev(3 * G);
     for (int r = 0; r < G; ++r) {
         Dev &d = m->dev[r];
         MCK(cudaSetDevice(d.device));
-        for (int k = 0; k < 3; ++k) MCK(cudaEventCreate(&ev[3 * r + k]));
         if ((size_t)G * pad > d.cap_all) {
             cudaFree(d.d_all); cudaFree(d.d_table);
             d.d_all = nullptr; d.d_table = nullptr;
@@ -339,7 +345,7 @@ extern "C" int blx_multi_nearest(blx_multi *m, int *nearest_index, float *neares
             MCK(cudaMalloc(&d.d_table, (size_t)G * pad * 16));
             d.cap_all = (size_t)G * pad;
         }
-        MCK(cudaEventRecord(ev[3 * r], d.st));
+        MCK(cudaEventRecord(d.ev[0], d.st));
     }
     // (1) all-gather of the padded blocks, device to device
     if (G == 1) {
@@ -372,25 +378,24 @@ extern "C" int blx_multi_nearest(blx_multi *m, int *nearest_index, float *neares
                 MCK(cudaMemcpyAsync(d.d_table + (size_t)lo * 4, d.d_all + (size_t)s * pad * 4, (size_t)(hi - lo) * 16,
                                     cudaMemcpyDeviceToDevice, d.st));
         }
-        MCK(cudaEventRecord(ev[3 * r + 1], d.st));
+        MCK(cudaEventRecord(d.ev[1], d.st));
         if (d.hi > d.lo) {
             int rc = blx_distance_nearest_device(d.eng, d.d_table, n, d.lo, d.hi - d.lo, d.d_idx, d.d_dist, nullptr, d.st);
             if (rc) return rc;
             if (nearest_index) MCK(cudaMemcpyAsync(nearest_index + d.lo, d.d_idx, (size_t)(d.hi - d.lo) * 4, cudaMemcpyDeviceToHost, d.st));
             if (nearest_dist) MCK(cudaMemcpyAsync(nearest_dist + d.lo, d.d_dist, (size_t)(d.hi - d.lo) * 4, cudaMemcpyDeviceToHost, d.st));
         }
-        MCK(cudaEventRecord(ev[3 * r + 2], d.st));
+        MCK(cudaEventRecord(d.ev[2], d.st));
     }
     float g_ms = 0, n_ms = 0;
     for (int r = 0; r < G; ++r) {
         MCK(cudaSetDevice(m->dev[r].device));
         MCK(cudaStreamSynchronize(m->dev[r].st));
         float a = 0, b = 0;
-        cudaEventElapsedTime(&a, ev[3 * r], ev[3 * r + 1]);
-        cudaEventElapsedTime(&b, ev[3 * r + 1], ev[3 * r + 2]);
+        cudaEventElapsedTime(&a, m->dev[r].ev[0], m->dev[r].ev[1]);
+        cudaEventElapsedTime(&b, m->dev[r].ev[1], m->dev[r].ev[2]);
         g_ms = std::max(g_ms, a);
         n_ms = std::max(n_ms, b);
-        for (int k = 0; k < 3; ++k) cudaEventDestroy(ev[3 * r + k]);
     }
     if (gather_ms) *gather_ms = g_ms;
     if (nearest_ms) *nearest_ms = n_ms;
