@@ -143,4 +143,22 @@ __device__ __forceinline__ void fft256_halfwarp(typename cplx<T>::type (&v)[16],
     fft16<T>(v);
 }
 
+// The same with the inter-pass twiddles of this lane already in registers: twr[c] = exp(-2 pi i lane16 c / 256), c = 1..15
+// (a kernel that walks many transforms loads them once; float only - 30 registers).
+template <typename T>
+__device__ __forceinline__ void fft256_halfwarp_regtw(typename cplx<T>::type (&v)[16], int lane16, typename cplx<T>::type *xchg,
+                                                      const typename cplx<T>::type (&twr)[16], unsigned mask) {
+    using C = typename cplx<T>::type;
+    fft16<T>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int c = fft16_out_index(r);
+        xchg[c * kXchgRow + lane16] = (c == 0) ? v[r] : cmul<C>(v[r], twr[c]);
+    }
+    __syncwarp(mask);
+#pragma unroll
+    for (int b = 0; b < 16; ++b) v[b] = xchg[lane16 * kXchgRow + b];
+    fft16<T>(v);
+}
+
 } // namespace blx

@@ -101,8 +101,19 @@ struct ThreadStats {
 };
 } // namespace
 
+#ifndef BLX_P1_TW_REG
+// 1: the 15 inter-pass FFT twiddles of a thread stay in registers for the life of the CTA (30 registers) instead of being
+// read from shared memory for every frame; the register allocation is sized for the CTAs per SM that shared memory allows
+#define BLX_P1_TW_REG 1
+#endif
+#if BLX_P1_TW_REG
+#define BLX_P1_BOUNDS __launch_bounds__(kP1Threads, (KIND == kInF32 ? 3 : 4) + (FULL ? 0 : 1)) // = what P1Smem<KIND> lets an SM hold
+#else
+#define BLX_P1_BOUNDS __launch_bounds__(kP1Threads)
+#endif
+
 template <int KIND, bool FULL>
-__global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant__ Pass1Params p) {
+__global__ void BLX_P1_BOUNDS pass1_kernel(const __grid_constant__ Pass1Params p) {
     using SM = P1Smem<KIND>;
     using G = RowGeom<KIND>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -132,6 +143,11 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant
         mbar_init(bar, 1);
         mbar_fence_init();
     }
+#if BLX_P1_TW_REG
+    float2 twr[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) twr[c] = p.tw1[c * 16 + lane16];
+#endif
     __syncthreads();
 
     const unsigned char *src = reinterpret_cast<const unsigned char *>(p.pcm) + (size_t)sd.pcm_off * G::ebytes;
@@ -431,7 +447,11 @@ __global__ void __launch_bounds__(kP1Threads) pass1_kernel(const __grid_constant
 #pragma unroll
             for (int a = 0; a < 16; ++a) v[a] = *reinterpret_cast<const float2 *>(fin + grp * kFinFrame + 36 * a + 2 * lane16);
             __syncwarp(full);
+#if BLX_P1_TW_REG
+            fft256_halfwarp_regtw<float>(v, lane16, xchg, twr, full);
+#else
             fft256_halfwarp<float>(v, lane16, xchg, tw1, full);
+#endif
             __syncwarp(full);
 #pragma unroll
             for (int r = 0; r < 16; ++r) xchg[lane16 + 16 * fft16_out_index(r)] = v[r];

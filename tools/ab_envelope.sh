@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 VAR=tools/variants
 declare -A FLAGS=(
   [base]=""
-  [pshfl]="-DBLX_ENV_PARTNER_SHFL=1"
+  [p1twsmem]="-DBLX_P1_TW_REG=0"
 )
 if [ "$1" = build ]; then
   mkdir -p $VAR
@@ -26,15 +26,17 @@ else
   songs=${2:-1024}
   for so in $VAR/libbliss_*.so; do
     v=$(basename $so .so)
-    BLX_DEBUG_OCCUPANCY=1 BLISS_B200_LIB=$PWD/$so python bench.py --steps 3 --warmup 2 --songs-per-step $songs --no-cpu --no-spectral --no-distance \
+    BLX_DEBUG_OCCUPANCY=1 BLISS_B200_LIB=$PWD/$so python bench.py --steps 3 --warmup 2 --songs-per-step $songs --no-cpu --no-distance \
       --e2e-songs 2 --s16-songs 128 --parity-songs 0 --chain-songs 0 --no-bl-analyze > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || echo "$v FAILED"
     grep -h "CTAs/SM" gpurun_out/ab_$v.err | head -1
     python - "$v" gpurun_out/ab_$v.json <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
 k = d["roofline_kernels"]
-print("%-18s env %.3f ms  pass1 %.3f  step %.2f ms  native_s16 %.0f songs/s" % (sys.argv[1], k["envelope_kernel"]["ms_per_step"],
-      k["pass1_kernel"]["ms_per_step"], d["ms_per_step"], d["native_s16"]["value"] if d.get("native_s16") else 0))
+sp = d.get("spectral_only") or {}
+print("%-18s env %.3f ms  pass1 %.3f  step %.2f ms  native_s16 %.0f songs/s  spectral %.0f songs/s frac %.3f" % (sys.argv[1],
+      k["envelope_kernel"]["ms_per_step"], k["pass1_kernel"]["ms_per_step"], d["ms_per_step"],
+      d["native_s16"]["value"] if d.get("native_s16") else 0, sp.get("value", 0), (sp.get("roofline") or {}).get("frac", 0)))
 PY
   done
 fi
