@@ -189,9 +189,20 @@ constexpr int kBox = 19;
 // kTailBlk sample pairs, warp 0 consumes them. Named barriers 1.. (full) and 1 + kTailBufs.. (empty).
 constexpr int kTailBlk = 8;      // input pairs (2 samples each) per ring block
 constexpr int kTailBufs = 4;
+// the two hand-overs between the owner and the IIR warp are named barriers as well, one warp arriving and the other
+// waiting: the warps reach them from different places in the code, which __syncthreads() (one call site for the whole
+// block) does not allow
+constexpr int kBarPublished = 1 + 2 * kTailBufs, kBarHandedBack = 2 + 2 * kTailBufs;
 
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kTailThreads) : "memory"); }
+// bar.sync / bar.arrive are warp-ALIGNED instructions: the whole warp has to execute them together. Both are used behind
+// per-lane `if (run_env)` blocks (a lane without a song idles), so the warp is re-converged first (compute-sanitizer
+// --tool synccheck flags the barrier otherwise; tools/sanitize.sh).
+__device__ __forceinline__ void bar_sync(int id) {
+    __syncwarp();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kTailThreads) : "memory");
+}
 __device__ __forceinline__ void bar_arrive(int id) {
+    __syncwarp();
     __threadfence_block(); // the ring block / its release is visible before the other warp passes its bar.sync
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(kTailThreads) : "memory");
 }
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
 
     if (role == 1) {
         // ---- IIR warp: y[n] for the piped phase (reference src/tempo_atk_sort.c:201-218, same operation order)
-        __syncthreads(); // the owners have run their start-up samples and published state + block count
+        bar_sync(kBarPublished); // the owners have run their start-up samples and published state + block count
         const int n_blocks = sh_blocks;
         const double *X = p.xlog + sd.env_off;
         double y1 = 0, y2 = 0, y3 = 0, y4 = 0, y5 = 0, y6 = 0, e1 = 0, e2 = 0, e3 = 0;
@@ -292,7 +303,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
             hand[0][tx] = y1; hand[1][tx] = y2; hand[2][tx] = y3; hand[3][tx] = y4; hand[4][tx] = y5; hand[5][tx] = y6;
             hand[6][tx] = e1; hand[7][tx] = e2; hand[8][tx] = e3;
         }
-        __syncthreads(); // state handed back
+        bar_arrive(kBarHandedBack); // state handed back (one-way: the owner warp waits for it)
         return;
     }
 
@@ -420,8 +431,8 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
                 hand[0][tx] = y1; hand[1][tx] = y2; hand[2][tx] = y3; hand[3][tx] = y4; hand[4][tx] = y5; hand[5][tx] = y6;
                 hand[6][tx] = e1; hand[7][tx] = e2; hand[8][tx] = e3;
             }
-            __syncthreads();
-            const int n_blocks = sh_blocks;
+            bar_arrive(kBarPublished); // one-way: the IIR warp waits for it (bar.sync)
+            const int n_blocks = (nblk == 0x7fffffff) ? 0 : nblk; // what lane 0 just published in sh_blocks
             for (int k = 0; k < kTailBufs && k < n_blocks; ++k) bar_arrive(1 + kTailBufs + k); // the ring starts empty
             for (int b = 0; b < n_blocks; ++b) {
                 const int slot = b % kTailBufs;
@@ -432,7 +443,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
                 }
                 if (b + kTailBufs < n_blocks) bar_arrive(1 + kTailBufs + slot); // released (only if it is needed again)
             }
-            __syncthreads(); // the IIR warp has handed its state back
+            bar_sync(kBarHandedBack); // the IIR warp has handed its state back
             if (run_env && n_blocks > 0) {
                 y1 = hand[0][tx]; y2 = hand[1][tx]; y3 = hand[2][tx]; y4 = hand[3][tx]; y5 = hand[4][tx]; y6 = hand[5][tx];
                 e1 = hand[6][tx]; e2 = hand[7][tx]; e3 = hand[8][tx];

@@ -1,0 +1,12 @@
+#!/bin/bash
+# compute-sanitizer over a small slice of the GPU suite (run on the GPU box): memcheck on the analysis + distance paths,
+# racecheck and synccheck on the kernels that exchange through shared memory. Logs under gpurun_out/.
+mkdir -p gpurun_out
+SEL='golden_fixture or hop_counts or ragged_batch or extreme or silent_passages or distance_nearest_matches or resampler_kernel'
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$SEL" > gpurun_out/san_memcheck.log 2>&1; echo "memcheck rc=$?"
+tail -4 gpurun_out/san_memcheck.log
+SEL2='golden_fixture or hop_counts'
+[ -n "$SKIP_RACE" ] || timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$SEL2" > gpurun_out/san_racecheck.log 2>&1; echo "racecheck rc=$?"
+tail -4 gpurun_out/san_racecheck.log
+timeout 900 compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$SEL" > gpurun_out/san_synccheck.log 2>&1; echo "synccheck rc=$?"
+tail -4 gpurun_out/san_synccheck.log
