@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 SEL='golden_fixture or hop_counts or ragged_batch or extreme or silent_passages or distance_nearest_matches or resampler_kernel'
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$SEL" > gpurun_out/san_memcheck.log 2>&1; echo "memcheck rc=$?"
 tail -4 gpurun_out/san_memcheck.log
-SEL2='golden_fixture or hop_counts'
+SEL2='golden_fixture or hop_counts or silence_f32 or spectrum_per_bin'
 [ -n "$SKIP_RACE" ] || timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$SEL2" > gpurun_out/san_racecheck.log 2>&1; echo "racecheck rc=$?"
 tail -4 gpurun_out/san_racecheck.log
 timeout 900 compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$SEL" > gpurun_out/san_synccheck.log 2>&1; echo "synccheck rc=$?"
