@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kEpThreads) epilogue_kernel(EpilogueParams p) 
     if (p.energy && (p.what & BLX_DO_ENVELOPE)) {
         __syncthreads();
         double *row = p.energy + sd.env_off;
-        const int nb = 2 * sd.F;
+        const int nb = (max(2 * sd.F, 2) + 7) & ~7; // the whole row incl. its padding (plan_songs): logcomp reads all of it
         for (int i = (sh_status ? 0 : max(sd.n_hops, 0)) + tid; i < nb; i += kEpThreads) row[i] = 0.0;
     }
 }
@@ -532,11 +532,12 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(TailParams p, int n_
 // Step 6 of the envelope analyser for every hop of every song at once (reference
 // src/tempo_atk_sort.c:186-190): x = log(1 + mu E) / log(1 + mu), mu = 100.0f. Element-wise over the
 // packed energy rows; the sequential tail then only streams x.
+// xlog carries 16 doubles of read-ahead slack behind the last row (the tail's prefetch); they are written as zeros.
 __global__ void logcomp_kernel(const double *__restrict__ energy, double *__restrict__ xlog, long long n) {
     const float mu = 100.0f;
     const double log_den = log((double)(1 + mu));
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        xlog[i] = log(1 + (double)mu * energy[i]) / log_den;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n + 16; i += (long long)gridDim.x * blockDim.x)
+        xlog[i] = (i < n) ? log(1 + (double)mu * energy[i]) / log_den : 0.0;
 }
 
 cudaError_t launch_logcomp(const double *d_energy, double *d_xlog, long long n, cudaStream_t st) {
