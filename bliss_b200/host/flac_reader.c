@@ -254,7 +254,10 @@ static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
     f->is_float = 0;
     f->container = 0;
 
+    /* STREAMINFO's sample count is a 36-bit field of an untrusted file: it sizes the first allocation only as far as the
+     * file could plausibly deliver (16 samples per byte); a longer stream grows the buffer as it is decoded. */
     size_t cap = total ? (size_t)total : (size_t)1 << 20;
+    if (cap > n * 16 + 65536) cap = n * 16 + 65536;
     int32_t *pcm = (int32_t *)malloc(cap * (size_t)f->channels * sizeof(int32_t));
     int32_t *chbuf = (int32_t *)malloc((size_t)65536 * 8 * sizeof(int32_t));
     if (!pcm || !chbuf) { free(pcm); free(chbuf); return -1; }
