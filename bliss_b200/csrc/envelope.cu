@@ -100,7 +100,10 @@ namespace blx {
 #endif
 
 namespace {
-constexpr int kPairsPerWarp = 32;                // a warp owns 64 consecutive hops
+#ifndef BLX_ENV_PAIRS
+#define BLX_ENV_PAIRS 32
+#endif
+constexpr int kPairsPerWarp = BLX_ENV_PAIRS;     // a warp owns 2 * kPairsPerWarp consecutive hops (64)
 constexpr int kSlotBytes = kHop * 8;             // one block of 256 FIR outputs (128 cells of 16 bytes)
 
 // Shared-memory plan. Per warp: the FFT exchange buffers of its two hops (the first 2 KB first hold

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 VAR=tools/variants
 declare -A FLAGS=(
   [base]=""
-  [p1twsmem]="-DBLX_P1_TW_REG=0"
+  [pshfl]="-DBLX_ENV_PARTNER_SHFL=1"
 )
 if [ "$1" = build ]; then
   mkdir -p $VAR
