@@ -24,32 +24,47 @@
 typedef struct {
     const uint8_t *p;
     size_t n;
-    size_t pos;   /* next byte to load */
-    uint64_t acc; /* bit accumulator, MSB-first, valid bits in the low `cnt` */
-    int cnt;
-    int err;
+    size_t pos;   /* next byte to load (runs past n at the end of the data: zeros are shifted in) */
+    uint64_t acc; /* bit window, MSB first: the next bit of the stream is bit 63; bits below the valid `cnt` are 0 */
+    int cnt;      /* valid bits in acc */
 } bitrd;
 
 static void br_init(bitrd *b, const uint8_t *p, size_t n, size_t pos) {
-    b->p = p; b->n = n; b->pos = pos; b->acc = 0; b->cnt = 0; b->err = 0;
+    b->p = p; b->n = n; b->pos = pos; b->acc = 0; b->cnt = 0;
 }
 
-static inline void br_fill(bitrd *b, int need) {
-    while (b->cnt < need) {
-        uint64_t byte = 0;
-        if (b->pos < b->n) byte = b->p[b->pos];
-        else b->err = 1;
+/* Tops the window up to at least 57 valid bits: one unaligned 8-byte load when the data allows, byte by byte at its end. */
+static inline void br_refill(bitrd *b) {
+    if (b->pos + 8 <= b->n) {
+        uint64_t w;
+        memcpy(&w, b->p + b->pos, 8);
+        w = __builtin_bswap64(w); /* little-endian host (as everywhere in this library) */
+        b->acc |= w >> b->cnt;
+        const int take = (63 - b->cnt) >> 3; /* whole bytes that fit */
+        b->pos += (size_t)take;
+        b->cnt += take * 8;
+        b->acc &= ~(~0ull >> b->cnt); /* the bits of the partly loaded next byte stay out of the window (56 <= cnt <= 63) */
+        return;
+    }
+    while (b->cnt <= 56) {
+        const uint64_t byte = (b->pos < b->n) ? b->p[b->pos] : 0;
         b->pos++;
-        b->acc = (b->acc << 8) | byte;
+        b->acc |= byte << (56 - b->cnt);
         b->cnt += 8;
     }
 }
 
+/* bytes of the stream consumed so far; more than n = the reader ran off the end of the data */
+static inline size_t br_bytepos(const bitrd *b) { return b->pos - (size_t)(b->cnt >> 3); }
+static inline int br_err(const bitrd *b) { return br_bytepos(b) > b->n; }
+
 static inline uint32_t br_u(bitrd *b, int nbits) { /* nbits <= 32 */
     if (nbits == 0) return 0;
-    br_fill(b, nbits);
+    if (b->cnt < nbits) br_refill(b);
+    const uint32_t v = (uint32_t)(b->acc >> (64 - nbits));
+    b->acc <<= nbits;
     b->cnt -= nbits;
-    return (uint32_t)((b->acc >> b->cnt) & ((nbits == 32) ? 0xFFFFFFFFu : ((1u << nbits) - 1u)));
+    return v;
 }
 
 static inline int32_t br_s(bitrd *b, int nbits) {
@@ -62,25 +77,27 @@ static inline int32_t br_s(bitrd *b, int nbits) {
 static inline uint32_t br_unary(bitrd *b) { /* count zeros before the next 1 bit */
     uint32_t z = 0;
     for (;;) {
-        if (b->cnt == 0) {
-            br_fill(b, 8);
-            if (b->err) return z;
-        }
-        uint64_t window = b->acc & ((b->cnt == 64) ? ~0ull : ((1ull << b->cnt) - 1ull));
-        if (window == 0) {
+        if (b->acc == 0) { /* only zeros in the window */
             z += (uint32_t)b->cnt;
             b->cnt = 0;
+            if (b->pos >= b->n + 8) return z; /* nothing but the padding behind the data: the caller sees br_err */
+            br_refill(b);
             continue;
         }
-        int top = 63 - __builtin_clzll(window); /* position of the first 1 */
-        z += (uint32_t)(b->cnt - 1 - top);
-        b->cnt = top;                          /* consume zeros and the 1 */
+        const int lz = __builtin_clzll(b->acc); /* < cnt: the bits below cnt are zero */
+        z += (uint32_t)lz;
+        b->acc <<= lz;   /* two shifts: lz + 1 may be 64 */
+        b->acc <<= 1;
+        b->cnt -= lz + 1;
         return z;
     }
 }
 
-static inline void br_align(bitrd *b) { b->cnt -= (b->cnt & 7); }
-static inline size_t br_bytepos(const bitrd *b) { return b->pos - (size_t)(b->cnt >> 3); }
+static inline void br_align(bitrd *b) {
+    const int drop = b->cnt & 7;
+    b->acc <<= drop;
+    b->cnt -= drop;
+}
 
 /* ------------------------------------------------------------------ */
 /* FLAC                                                                */
@@ -96,22 +113,36 @@ static uint8_t crc8_of(const uint8_t *p, size_t n) {
     }
     return c;
 }
-static uint16_t crc16_of(const uint8_t *p, size_t n) {
-    static uint16_t tab[256];
-    static int ready = 0;
-    if (!ready) {
-        for (int i = 0; i < 256; ++i) {
-            uint16_t c = (uint16_t)(i << 8);
-            for (int k = 0; k < 8; ++k) c = (uint16_t)((c & 0x8000) ? (c << 1) ^ 0x8005 : (c << 1));
-            tab[i] = c;
-        }
-        ready = 1;
+/* CRC-16, eight bytes per step (slicing-by-8): tab[k][b] = the CRC of byte b followed by k zero bytes. The tables are
+ * filled once when the library is loaded (no lazy initialisation that concurrent callers could race on). */
+static uint16_t crc16_tab[8][256];
+__attribute__((constructor)) static void crc16_init(void) {
+    for (int i = 0; i < 256; ++i) {
+        uint16_t c = (uint16_t)(i << 8);
+        for (int k = 0; k < 8; ++k) c = (uint16_t)((c & 0x8000) ? (c << 1) ^ 0x8005 : (c << 1));
+        crc16_tab[0][i] = c;
     }
+    for (int k = 1; k < 8; ++k)
+        for (int i = 0; i < 256; ++i) {
+            const uint16_t c = crc16_tab[k - 1][i];
+            crc16_tab[k][i] = (uint16_t)((c << 8) ^ crc16_tab[0][c >> 8]);
+        }
+}
+static uint16_t crc16_of(const uint8_t *p, size_t n) {
     uint16_t c = 0;
-    for (size_t i = 0; i < n; ++i) c = (uint16_t)((c << 8) ^ tab[(c >> 8) ^ p[i]]);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        const uint8_t b0 = (uint8_t)(p[i] ^ (c >> 8)), b1 = (uint8_t)(p[i + 1] ^ (c & 0xFF));
+        c = (uint16_t)(crc16_tab[7][b0] ^ crc16_tab[6][b1] ^ crc16_tab[5][p[i + 2]] ^ crc16_tab[4][p[i + 3]] ^ crc16_tab[3][p[i + 4]] ^
+                       crc16_tab[2][p[i + 5]] ^ crc16_tab[1][p[i + 6]] ^ crc16_tab[0][p[i + 7]]);
+    }
+    for (; i < n; ++i) c = (uint16_t)((c << 8) ^ crc16_tab[0][(c >> 8) ^ p[i]]);
     return c;
 }
 
+#ifndef BLX_RICE_FAST
+#define BLX_RICE_FAST 1
+#endif
 static int read_residual(bitrd *b, int32_t *out, int blocksize, int pred_order) {
     int method = (int)br_u(b, 2);
     if (method > 1) return -1;
@@ -130,15 +161,67 @@ static int read_residual(bitrd *b, int32_t *out, int blocksize, int pred_order) 
             for (int i = 0; i < count; ++i) out[idx++] = br_s(b, raw);
         } else {
             for (int i = 0; i < count; ++i) {
-                uint32_t q = br_unary(b);
-                uint32_t r = br_u(b, (int)param);
-                uint32_t u = (q << param) | r;
+                uint32_t u;
+                if (b->cnt < 57) br_refill(b);
+                if (BLX_RICE_FAST && param <= 16 && (b->acc >> 24) != 0) {
+                    /* the usual case in one go: fewer than 40 zeros, the stop bit and the low bits all sit in the window */
+                    const int lz = __builtin_clzll(b->acc);
+                    const uint64_t rest = b->acc << lz << 1;
+                    const uint32_t r = (uint32_t)((rest >> 32) >> (32 - param)); /* param = 0: a 32-bit word shifted out whole */
+                    u = ((uint32_t)lz << param) | (param ? r : 0u);
+                    b->acc = rest << param;
+                    b->cnt -= lz + 1 + (int)param;
+                } else {
+                    const uint32_t q = br_unary(b);
+                    const uint32_t r = br_u(b, (int)param);
+                    u = (q << param) | r;
+                }
                 out[idx++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
             }
         }
-        if (b->err) return -1;
+        if (br_err(b)) return -1;
     }
     return 0;
+}
+
+/* LPC synthesis out[i] += (sum_j coef[j] out[i - 1 - j]) >> shift, i = order..n-1 (RFC 9639 section 9.2.6), the inner
+ * loop of the decoder: the taps are reversed once so that the dot product runs over contiguous samples, the common
+ * orders get a loop with a constant trip count (unrolled and vectorised by the compiler; an AVX2 clone is picked at
+ * load time where the CPU has it), and 32-bit accumulators are used when bps + precision + log2(order) <= 32 bits
+ * guarantees that nothing overflows them. */
+static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+/* (the 32-bit form works on unsigned words, so a damaged file whose samples outgrow their declared width wraps around
+ * instead of running into signed overflow) */
+#define BLX_LPC_BODY(ACC_T, ORD)                                                               \
+    for (int i = order; i < n; ++i) {                                                          \
+        ACC_T acc = 0;                                                                         \
+        const int32_t *h = out + i - (ORD);                                                    \
+        for (int k = 0; k < (ORD); ++k) acc += (ACC_T)rc[k] * (ACC_T)h[k];                     \
+        if (sizeof(ACC_T) == 4) out[i] = (int32_t)((uint32_t)((int32_t)acc >> shift) + (uint32_t)out[i]); \
+        else out[i] = (int32_t)(((int64_t)acc >> shift) + out[i]);                             \
+    }
+#define BLX_LPC_SWITCH(ACC_T)                                                                  \
+    switch (order) {                                                                           \
+        case 1: BLX_LPC_BODY(ACC_T, 1) break;   case 2: BLX_LPC_BODY(ACC_T, 2) break;          \
+        case 3: BLX_LPC_BODY(ACC_T, 3) break;   case 4: BLX_LPC_BODY(ACC_T, 4) break;          \
+        case 5: BLX_LPC_BODY(ACC_T, 5) break;   case 6: BLX_LPC_BODY(ACC_T, 6) break;          \
+        case 7: BLX_LPC_BODY(ACC_T, 7) break;   case 8: BLX_LPC_BODY(ACC_T, 8) break;          \
+        case 9: BLX_LPC_BODY(ACC_T, 9) break;   case 10: BLX_LPC_BODY(ACC_T, 10) break;        \
+        case 11: BLX_LPC_BODY(ACC_T, 11) break; case 12: BLX_LPC_BODY(ACC_T, 12) break;        \
+        default: BLX_LPC_BODY(ACC_T, order) break;                                             \
+    }
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define BLX_CLONES __attribute__((target_clones("avx2", "default"), optimize("O3")))
+#else
+#define BLX_CLONES
+#endif
+BLX_CLONES static void lpc_restore(int32_t *out, int n, int order, const int32_t *coef, int shift, int narrow) {
+    int32_t rc[32];
+    for (int k = 0; k < order; ++k) rc[k] = coef[order - 1 - k];
+    if (narrow) { BLX_LPC_SWITCH(uint32_t) }
+    else { BLX_LPC_SWITCH(int64_t) }
 }
 
 static int read_subframe(bitrd *b, int32_t *out, int blocksize, int bps) {
@@ -181,17 +264,13 @@ static int read_subframe(bitrd *b, int32_t *out, int blocksize, int bps) {
         if (shift < 0) return -1;
         for (int i = 0; i < order; ++i) coef[i] = br_s(b, prec);
         if (read_residual(b, out, blocksize, order)) return -1;
-        for (int i = order; i < blocksize; ++i) {
-            int64_t acc = 0;
-            for (int j = 0; j < order; ++j) acc += (int64_t)coef[j] * out[i - 1 - j];
-            out[i] = (int32_t)((acc >> shift) + out[i]);
-        }
+        lpc_restore(out, blocksize, order, coef, shift, bps + prec + ilog2_ceil(order) <= 32);
     } else {
         return -1;
     }
     if (wasted)
         for (int i = 0; i < blocksize; ++i) out[i] = (int32_t)((uint32_t)out[i] << wasted);
-    return b->err ? -1 : 0;
+    return br_err(b) ? -1 : 0;
 }
 
 static void add_tag(blx_pcm_file *f, const char *kv, size_t len) {
@@ -290,12 +369,12 @@ static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
         {
             const size_t hdr_end = br_bytepos(&b);
             const uint32_t crc8 = br_u(&b, 8);
-            if (b.err || hdr_end > n || crc8 != crc8_of(d + pos, hdr_end - pos)) { pos++; continue; } /* a false sync */
+            if (br_err(&b) || hdr_end > n || crc8 != crc8_of(d + pos, hdr_end - pos)) { pos++; continue; } /* a false sync */
         }
         static const int ss_tab[8] = {0, 8, 12, 0, 16, 20, 24, 32};
         int bps = ss_tab[ss_code] ? ss_tab[ss_code] : f->bits_per_sample;
         int nch = (ch_code < 8) ? ch_code + 1 : 2;
-        if (ch_code > 10 || nch != f->channels || b.err) { pos++; continue; }
+        if (ch_code > 10 || nch != f->channels || br_err(&b)) { pos++; continue; }
 
         int ok = 1;
         for (int c = 0; c < nch && ok; ++c) {
@@ -307,7 +386,7 @@ static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
         {
             const size_t body_end = br_bytepos(&b);
             const uint32_t crc16 = br_u(&b, 16);
-            if (b.err) break;
+            if (br_err(&b)) break;
             if (crc16 != crc16_of(d + pos, body_end - pos)) { pos++; continue; } /* damaged frame: resynchronise */
         }
 
