@@ -1,0 +1,54 @@
+"""The host FLAC decoder (bliss_b200/host/flac_reader.c) against streams built by tests/flac_encode.py: every subframe
+type, LPC orders 1..32 (the specialised loops and the generic one), 32- and 64-bit synthesis, wasted bits, escaped and
+5-bit Rice partitions, partition orders, all stereo modes, 8..24-bit samples, short last block. Decoding must give back
+the PCM exactly. (The reference's own fixtures pin the decoder against libFLAC-encoded files: test_oracle.py.)"""
+import numpy as np
+import pytest
+
+from flac_encode import encode
+from flac_util import read_pcm_file
+
+
+def _signal(rng, n, ch, bps):
+    t = np.arange(n)
+    amp = (1 << (bps - 1)) * 0.6
+    x = np.stack([amp * (0.5 * np.sin(2 * np.pi * t / rng.uniform(20, 400)) + 0.2 * rng.standard_normal(n)) for _ in range(ch)], axis=1)
+    if ch == 2:
+        x[:, 1] = 0.7 * x[:, 0] + 0.3 * x[:, 1]  # correlated channels, as real stereo is
+    return np.clip(np.round(x), -(1 << (bps - 1)), (1 << (bps - 1)) - 1).astype(np.int64)
+
+
+KINDS = ["lpc", "fixed0", "fixed1", "fixed2", "fixed3", "fixed4", "verbatim", "constant"]
+
+
+@pytest.mark.parametrize("bps,ch", [(8, 1), (12, 2), (16, 1), (16, 2), (20, 2), (24, 1), (24, 2)])
+def test_roundtrip_all_subframe_kinds(tmp_path, bps, ch):
+    rng = np.random.default_rng(bps * 10 + ch)
+    blocksize = 1152
+    n = blocksize * 40 + 333  # a short last block
+    pcm = _signal(rng, n, ch, bps)
+    pcm[blocksize * 7:blocksize * 8] = pcm[blocksize * 7]       # a constant block
+    pcm[blocksize * 9:blocksize * 10] &= ~7                       # a block with three wasted bits
+    orders = list(range(1, 33))
+
+    def plan(fi):
+        return dict(kind="constant" if fi == 7 else KINDS[fi % 7], stereo=[None, 8, 9, 10][fi % 4] if ch == 2 else None,
+                    lpc_order=orders[(fi * 5) % 32], method=fi % 2, porder=[0, 1, 3, 5][fi % 4 if blocksize % 32 == 0 else 0],
+                    escape_parts=(0,) if fi % 6 == 5 else (), wasted=3 if fi == 9 else 0)
+
+    path = tmp_path / "t.flac"
+    path.write_bytes(encode(pcm, bps, 22050, blocksize, plan, seed=bps + ch))
+    got, n_frames, channels, rate, bits = read_pcm_file(path)
+    assert (n_frames, channels, rate, bits) == (n, ch, 22050, bps)
+    assert np.array_equal(got.reshape(-1, ch), pcm)
+
+
+def test_every_lpc_order_narrow_and_wide(tmp_path):
+    for bps in (16, 24):
+        rng = np.random.default_rng(bps)
+        blocksize = 512
+        pcm = _signal(rng, blocksize * 32, 2, bps)
+        path = tmp_path / f"o{bps}.flac"
+        path.write_bytes(encode(pcm, bps, 44100, blocksize, lambda fi: dict(kind="lpc", lpc_order=fi + 1, stereo=10, porder=2), seed=bps))
+        got = read_pcm_file(path)[0]
+        assert np.array_equal(got.reshape(-1, 2), pcm), bps
