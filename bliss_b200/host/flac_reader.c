@@ -13,6 +13,7 @@
  */
 #include "flac_reader.h"
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -212,7 +213,7 @@ static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
         default: BLX_LPC_BODY(ACC_T, order) break;                                             \
     }
 
-#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(__SANITIZE_THREAD__) /* (TSan cannot run ifunc resolvers) */
 #define BLX_CLONES __attribute__((target_clones("avx2", "default"), optimize("O3")))
 #else
 #define BLX_CLONES
@@ -290,6 +291,251 @@ static void add_tag(blx_pcm_file *f, const char *kv, size_t len) {
     }
 }
 
+/* ---- frames ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    size_t off;        /* byte offset of the sync code */
+    size_t hdr_len;    /* header bytes incl. CRC-8 */
+    int blocksize, ch_code, bps;
+    int variable;      /* blocking strategy bit: the coded number counts samples, not frames */
+    uint64_t number;   /* coded frame / sample number */
+} flac_hdr;
+
+/* Parses and checks (CRC-8, channel count) the frame header at d[pos]; 0 if there is a plausible one. */
+static int parse_frame_header(const uint8_t *d, size_t n, size_t pos, const blx_pcm_file *f, flac_hdr *h) {
+    if (pos + 6 > n || d[pos] != 0xFF || (d[pos + 1] & 0xFE) != 0xF8) return -1;
+    bitrd b;
+    br_init(&b, d, n, pos);
+    br_u(&b, 15);
+    h->variable = (int)br_u(&b, 1);
+    const int bs_code = (int)br_u(&b, 4);
+    const int sr_code = (int)br_u(&b, 4);
+    h->ch_code = (int)br_u(&b, 4);
+    const int ss_code = (int)br_u(&b, 3);
+    br_u(&b, 1);
+    /* UTF-8 style coded frame / sample number (up to 36 bits) */
+    const uint32_t first = br_u(&b, 8);
+    int extra = 0;
+    uint64_t num = first;
+    if (first & 0x80) {
+        uint32_t m = 0x40;
+        while (first & m) { extra++; m >>= 1; }
+        if (extra == 0 || extra > 6) return -1;
+        num = first & (m - 1);
+    }
+    for (int i = 0; i < extra; ++i) num = (num << 6) | (br_u(&b, 8) & 0x3F);
+    h->number = num;
+    if (bs_code == 1) h->blocksize = 192;
+    else if (bs_code >= 2 && bs_code <= 5) h->blocksize = 576 << (bs_code - 2);
+    else if (bs_code == 6) h->blocksize = (int)br_u(&b, 8) + 1;
+    else if (bs_code == 7) h->blocksize = (int)br_u(&b, 16) + 1;
+    else if (bs_code >= 8) h->blocksize = 256 << (bs_code - 8);
+    else return -1;
+    if (sr_code == 12) br_u(&b, 8);
+    else if (sr_code == 13 || sr_code == 14) br_u(&b, 16);
+    const size_t hdr_end = br_bytepos(&b);
+    const uint32_t crc8 = br_u(&b, 8);
+    if (br_err(&b) || hdr_end > n || crc8 != crc8_of(d + pos, hdr_end - pos)) return -1; /* a false sync */
+    static const int ss_tab[8] = {0, 8, 12, 0, 16, 20, 24, 32};
+    h->bps = ss_tab[ss_code] ? ss_tab[ss_code] : f->bits_per_sample;
+    const int nch = (h->ch_code < 8) ? h->ch_code + 1 : 2;
+    if (h->ch_code > 10 || nch != f->channels) return -1;
+    h->off = pos;
+    h->hdr_len = hdr_end + 1 - pos;
+    return 0;
+}
+
+/* Decodes the frame whose (checked) header is h into chbuf (channel c at chbuf + c * 65536), stereo decorrelation
+ * undone; *end = the byte behind its CRC-16. 0 = good frame, 1 = damaged (resynchronise), -1 = ran off the data. */
+static int decode_frame(const uint8_t *d, size_t n, const flac_hdr *h, int32_t *chbuf, size_t *end) {
+    bitrd b;
+    br_init(&b, d, n, h->off + h->hdr_len);
+    const int nch = (h->ch_code < 8) ? h->ch_code + 1 : 2, blocksize = h->blocksize;
+    for (int c = 0; c < nch; ++c) {
+        const int side = (h->ch_code == 8 && c == 1) || (h->ch_code == 9 && c == 0) || (h->ch_code == 10 && c == 1);
+        if (read_subframe(&b, chbuf + (size_t)c * 65536, blocksize, h->bps + side)) return 1;
+    }
+    br_align(&b);
+    const size_t body_end = br_bytepos(&b);
+    const uint32_t crc16 = br_u(&b, 16);
+    if (br_err(&b)) return -1;
+    if (crc16 != crc16_of(d + h->off, body_end - h->off)) return 1;
+    int32_t *c0 = chbuf, *c1 = chbuf + 65536;
+    if (h->ch_code == 8) { for (int i = 0; i < blocksize; ++i) c1[i] = c0[i] - c1[i]; }
+    else if (h->ch_code == 9) { for (int i = 0; i < blocksize; ++i) c0[i] = c0[i] + c1[i]; }
+    else if (h->ch_code == 10) {
+        for (int i = 0; i < blocksize; ++i) {
+            const int32_t side = c1[i];
+            const int32_t mid = (int32_t)(((uint32_t)c0[i] << 1) | (uint32_t)(side & 1));
+            c0[i] = (mid + side) >> 1;
+            c1[i] = (mid - side) >> 1;
+        }
+    }
+    *end = br_bytepos(&b);
+    return 0;
+}
+
+static void interleave(int32_t *dst, const int32_t *chbuf, int blocksize, int nch) {
+    if (nch == 2) {
+        const int32_t *c0 = chbuf, *c1 = chbuf + 65536;
+        for (int i = 0; i < blocksize; ++i) { dst[2 * i] = c0[i]; dst[2 * i + 1] = c1[i]; }
+    } else {
+        for (int i = 0; i < blocksize; ++i)
+            for (int c = 0; c < nch; ++c) dst[(size_t)i * (size_t)nch + (size_t)c] = chbuf[(size_t)c * 65536 + (size_t)i];
+    }
+}
+
+/* ---- parallel decode: the frames of a stream are independent ------------------------------------------------------ */
+typedef struct {
+    const uint8_t *d;
+    size_t n;
+    const flac_hdr *hdr;     /* the chain of frames found by the scan */
+    const size_t *first;     /* first sample (per channel) of every frame */
+    size_t n_frames;
+    int nch;
+    int32_t *pcm;
+    size_t next;             /* next frame nobody has taken (guarded by lock) */
+    int failed;              /* a frame did not decode or did not end where the next one starts */
+    pthread_mutex_t lock;
+} flac_job;
+
+static void *flac_worker(void *arg) {
+    flac_job *j = (flac_job *)arg;
+    int32_t *chbuf = (int32_t *)malloc((size_t)65536 * 8 * sizeof(int32_t));
+    for (;;) {
+        pthread_mutex_lock(&j->lock);
+        const size_t lo = j->next;
+        size_t hi = lo + 16; /* a batch of frames per visit */
+        if (hi > j->n_frames) hi = j->n_frames;
+        j->next = hi;
+        const int stop = j->failed || !chbuf;
+        if (!chbuf) j->failed = 1;
+        pthread_mutex_unlock(&j->lock);
+        if (lo >= hi || stop) break;
+        for (size_t k = lo; k < hi; ++k) {
+            size_t end = 0;
+            const size_t want = (k + 1 < j->n_frames) ? j->hdr[k + 1].off : 0;
+            if (decode_frame(j->d, j->n, &j->hdr[k], chbuf, &end) != 0 || (want && end != want)) {
+                pthread_mutex_lock(&j->lock);
+                j->failed = 1;
+                pthread_mutex_unlock(&j->lock);
+                break;
+            }
+            interleave(j->pcm + j->first[k] * (size_t)j->nch, chbuf, j->hdr[k].blocksize, j->nch);
+        }
+    }
+    free(chbuf);
+    return NULL;
+}
+
+static int flac_decode_threads(void) {
+    const char *e = getenv("BLX_DECODE_THREADS");
+    int t = e ? atoi(e) : 4;
+    return t < 1 ? 1 : (t > 32 ? 32 : t);
+}
+
+/* Finds the chain of frames by their headers alone (sync code, CRC-8, coded numbers that continue the sequence), decodes
+ * them on several threads and checks on the way that every frame is good and ends exactly where the next begins.
+ * 0 = done (f filled); anything unusual (a damaged or foreign byte range, a false sync that fits the sequence, numbers that
+ * jump) returns 1 and the caller decodes the stream sequentially, which resynchronises frame by frame. */
+static int decode_flac_parallel(const uint8_t *d, size_t n, size_t pos, uint64_t total, blx_pcm_file *f, int threads) {
+    size_t cap = 1024, nf = 0;
+    flac_hdr *hdr = (flac_hdr *)malloc(cap * sizeof(flac_hdr));
+    size_t *first = NULL;
+    int rc = 1;
+    if (!hdr) return 1;
+    size_t samples = 0;
+    while (pos + 6 <= n) {
+        const uint8_t *q = (const uint8_t *)memchr(d + pos, 0xFF, n - pos);
+        if (!q) break;
+        pos = (size_t)(q - d);
+        flac_hdr h;
+        if (parse_frame_header(d, n, pos, f, &h) != 0) { pos++; continue; }
+        if (nf) { /* must continue the sequence: a sync code inside a frame's data almost never does */
+            const flac_hdr *p = &hdr[nf - 1];
+            const uint64_t expect = p->variable ? p->number + (uint64_t)p->blocksize : p->number + 1;
+            if (h.variable != p->variable || h.number != expect) { pos++; continue; }
+        }
+        if (nf == cap) {
+            cap *= 2;
+            flac_hdr *nh = (flac_hdr *)realloc(hdr, cap * sizeof(flac_hdr));
+            if (!nh) goto out;
+            hdr = nh;
+        }
+        hdr[nf++] = h;
+        samples += (size_t)h.blocksize;
+        pos += h.hdr_len; /* (a frame is longer than its header: the next candidate cannot start inside it) */
+    }
+    if (nf < 32 || samples > ((size_t)1 << 40)) goto out;
+    first = (size_t *)malloc(nf * sizeof(size_t));
+    if (!first) goto out;
+    for (size_t k = 0, s = 0; k < nf; ++k) { first[k] = s; s += (size_t)hdr[k].blocksize; }
+    {
+        flac_job job;
+        memset(&job, 0, sizeof(job));
+        job.d = d; job.n = n; job.hdr = hdr; job.first = first; job.n_frames = nf; job.nch = f->channels;
+        job.pcm = (int32_t *)malloc(samples * (size_t)f->channels * sizeof(int32_t));
+        if (!job.pcm) goto out;
+        pthread_mutex_init(&job.lock, NULL);
+        pthread_t th[32];
+        int started = 0;
+        for (int t = 0; t < threads - 1; ++t)
+            if (pthread_create(&th[started], NULL, flac_worker, &job) == 0) started++;
+        flac_worker(&job); /* the calling thread works too */
+        for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+        pthread_mutex_destroy(&job.lock);
+        if (job.failed) { free(job.pcm); goto out; }
+        size_t nframes = samples;
+        if (total && nframes > total) nframes = (size_t)total;
+        f->samples = job.pcm;
+        f->n_frames = nframes;
+        rc = nframes ? 0 : 1;
+        if (rc) { free(job.pcm); f->samples = NULL; }
+    }
+out:
+    free(hdr);
+    free(first);
+    return rc;
+}
+
+/* The audio frames from d[pos] on. */
+static int decode_flac_frames(const uint8_t *d, size_t n, size_t pos, uint64_t total, blx_pcm_file *f) {
+    const int threads = flac_decode_threads();
+    if (threads > 1 && n - pos >= ((size_t)1 << 18) && decode_flac_parallel(d, n, pos, total, f, threads) == 0) return 0;
+
+    /* sequential: one frame after the other, resynchronising on the next good header after anything that is not a frame */
+    /* STREAMINFO's sample count is a 36-bit field of an untrusted file: it sizes the first allocation only as far as the
+     * file could plausibly deliver (16 samples per byte); a longer stream grows the buffer as it is decoded. */
+    size_t cap = total ? (size_t)total : (size_t)1 << 20;
+    if (cap > n * 16 + 65536) cap = n * 16 + 65536;
+    int32_t *pcm = (int32_t *)malloc(cap * (size_t)f->channels * sizeof(int32_t));
+    int32_t *chbuf = (int32_t *)malloc((size_t)65536 * 8 * sizeof(int32_t));
+    if (!pcm || !chbuf) { free(pcm); free(chbuf); return -1; }
+    size_t nframes = 0;
+    const int nch = f->channels;
+    while (pos + 2 <= n) {
+        flac_hdr h;
+        if (parse_frame_header(d, n, pos, f, &h) != 0) { pos++; continue; }
+        size_t end = 0;
+        const int fr = decode_frame(d, n, &h, chbuf, &end);
+        if (fr < 0) break;
+        if (fr > 0) { pos++; continue; } /* damaged frame: resynchronise */
+        if (nframes + (size_t)h.blocksize > cap) {
+            cap = (nframes + (size_t)h.blocksize) * 2;
+            int32_t *np = (int32_t *)realloc(pcm, cap * (size_t)nch * sizeof(int32_t));
+            if (!np) { free(pcm); free(chbuf); return -1; }
+            pcm = np;
+        }
+        interleave(pcm + nframes * (size_t)nch, chbuf, h.blocksize, nch);
+        nframes += (size_t)h.blocksize;
+        pos = end;
+    }
+    free(chbuf);
+    if (total && nframes > total) nframes = (size_t)total;
+    f->samples = pcm;
+    f->n_frames = nframes;
+    return nframes ? 0 : -1;
+}
+
 static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
     size_t pos = 4;
     int have_info = 0, last = 0;
@@ -332,92 +578,7 @@ static int decode_flac(const uint8_t *d, size_t n, blx_pcm_file *f) {
     if (!have_info || f->channels < 1 || f->channels > 8) return -1;
     f->is_float = 0;
     f->container = 0;
-
-    /* STREAMINFO's sample count is a 36-bit field of an untrusted file: it sizes the first allocation only as far as the
-     * file could plausibly deliver (16 samples per byte); a longer stream grows the buffer as it is decoded. */
-    size_t cap = total ? (size_t)total : (size_t)1 << 20;
-    if (cap > n * 16 + 65536) cap = n * 16 + 65536;
-    int32_t *pcm = (int32_t *)malloc(cap * (size_t)f->channels * sizeof(int32_t));
-    int32_t *chbuf = (int32_t *)malloc((size_t)65536 * 8 * sizeof(int32_t));
-    if (!pcm || !chbuf) { free(pcm); free(chbuf); return -1; }
-    size_t nframes = 0;
-
-    while (pos + 2 <= n) {
-        if (!(d[pos] == 0xFF && (d[pos + 1] & 0xFE) == 0xF8)) { pos++; continue; }
-        bitrd b;
-        br_init(&b, d, n, pos);
-        br_u(&b, 16);
-        int bs_code = (int)br_u(&b, 4);
-        int sr_code = (int)br_u(&b, 4);
-        int ch_code = (int)br_u(&b, 4);
-        int ss_code = (int)br_u(&b, 3);
-        br_u(&b, 1);
-        /* UTF-8 style coded frame/sample number */
-        uint32_t first = br_u(&b, 8);
-        int extra = 0;
-        if (first & 0x80) { uint32_t m = 0x40; while (first & m) { extra++; m >>= 1; } }
-        for (int i = 0; i < extra; ++i) br_u(&b, 8);
-        int blocksize;
-        if (bs_code == 1) blocksize = 192;
-        else if (bs_code >= 2 && bs_code <= 5) blocksize = 576 << (bs_code - 2);
-        else if (bs_code == 6) blocksize = (int)br_u(&b, 8) + 1;
-        else if (bs_code == 7) blocksize = (int)br_u(&b, 16) + 1;
-        else if (bs_code >= 8) blocksize = 256 << (bs_code - 8);
-        else { pos++; continue; }
-        if (sr_code == 12) br_u(&b, 8);
-        else if (sr_code == 13 || sr_code == 14) br_u(&b, 16);
-        {
-            const size_t hdr_end = br_bytepos(&b);
-            const uint32_t crc8 = br_u(&b, 8);
-            if (br_err(&b) || hdr_end > n || crc8 != crc8_of(d + pos, hdr_end - pos)) { pos++; continue; } /* a false sync */
-        }
-        static const int ss_tab[8] = {0, 8, 12, 0, 16, 20, 24, 32};
-        int bps = ss_tab[ss_code] ? ss_tab[ss_code] : f->bits_per_sample;
-        int nch = (ch_code < 8) ? ch_code + 1 : 2;
-        if (ch_code > 10 || nch != f->channels || br_err(&b)) { pos++; continue; }
-
-        int ok = 1;
-        for (int c = 0; c < nch && ok; ++c) {
-            int side = (ch_code == 8 && c == 1) || (ch_code == 9 && c == 0) || (ch_code == 10 && c == 1);
-            if (read_subframe(&b, chbuf + (size_t)c * 65536, blocksize, bps + side)) ok = 0;
-        }
-        if (!ok) { pos++; continue; }
-        br_align(&b);
-        {
-            const size_t body_end = br_bytepos(&b);
-            const uint32_t crc16 = br_u(&b, 16);
-            if (br_err(&b)) break;
-            if (crc16 != crc16_of(d + pos, body_end - pos)) { pos++; continue; } /* damaged frame: resynchronise */
-        }
-
-        int32_t *c0 = chbuf, *c1 = chbuf + 65536;
-        if (ch_code == 8) { for (int i = 0; i < blocksize; ++i) c1[i] = c0[i] - c1[i]; }
-        else if (ch_code == 9) { for (int i = 0; i < blocksize; ++i) c0[i] = c0[i] + c1[i]; }
-        else if (ch_code == 10) {
-            for (int i = 0; i < blocksize; ++i) {
-                int32_t side = c1[i];
-                int32_t mid = (int32_t)(((uint32_t)c0[i] << 1) | (uint32_t)(side & 1));
-                c0[i] = (mid + side) >> 1;
-                c1[i] = (mid - side) >> 1;
-            }
-        }
-        if (nframes + (size_t)blocksize > cap) {
-            cap = (nframes + (size_t)blocksize) * 2;
-            int32_t *np = (int32_t *)realloc(pcm, cap * (size_t)nch * sizeof(int32_t));
-            if (!np) { free(pcm); free(chbuf); return -1; }
-            pcm = np;
-        }
-        for (int i = 0; i < blocksize; ++i)
-            for (int c = 0; c < nch; ++c)
-                pcm[(nframes + (size_t)i) * (size_t)nch + (size_t)c] = chbuf[(size_t)c * 65536 + (size_t)i];
-        nframes += (size_t)blocksize;
-        pos = br_bytepos(&b);
-    }
-    free(chbuf);
-    if (total && nframes > total) nframes = (size_t)total;
-    f->samples = pcm;
-    f->n_frames = nframes;
-    return nframes ? 0 : -1;
+    return decode_flac_frames(d, n, pos, total, f);
 }
 
 /* ------------------------------------------------------------------ */

@@ -52,3 +52,26 @@ def test_every_lpc_order_narrow_and_wide(tmp_path):
         path.write_bytes(encode(pcm, bps, 44100, blocksize, lambda fi: dict(kind="lpc", lpc_order=fi + 1, stereo=10, porder=2), seed=bps))
         got = read_pcm_file(path)[0]
         assert np.array_equal(got.reshape(-1, 2), pcm), bps
+
+
+def test_threaded_decode_equals_sequential(tmp_path, monkeypatch):
+    """Frames are independent: a large stream is decoded on several threads (flac_reader.c: decode_flac_parallel, chain of
+    frames found by header CRC and coded numbers). Same samples as the sequential decoder, for intact files and - through
+    the fall-back - for a file with a damaged frame and one with foreign bytes spliced in."""
+    import os
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    files = [os.path.join(golden, "song.flac"), os.path.join(golden, "song_s32.flac")]
+    blob = bytearray(open(files[0], "rb").read())
+    blob[len(blob) // 2] ^= 0x55                       # one damaged frame: dropped by both decoders
+    (tmp_path / "damaged.flac").write_bytes(bytes(blob))
+    blob = bytearray(open(files[0], "rb").read())
+    blob[200000:200000] = bytes(range(256)) * 8         # 2 KB of foreign data between / inside frames
+    (tmp_path / "spliced.flac").write_bytes(bytes(blob))
+    files += [str(tmp_path / "damaged.flac"), str(tmp_path / "spliced.flac")]
+    for path in files:
+        monkeypatch.setenv("BLX_DECODE_THREADS", "1")
+        ref = read_pcm_file(path)
+        for threads in ("2", "8"):
+            monkeypatch.setenv("BLX_DECODE_THREADS", threads)
+            got = read_pcm_file(path)
+            assert got[1:] == ref[1:] and np.array_equal(got[0], ref[0]), (path, threads)
