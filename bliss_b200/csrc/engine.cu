@@ -831,8 +831,8 @@ extern "C" int blx_frontend_f32(blx_engine *e, const float *pcm, int64_t n_in, i
     return BLX_OK;
 }
 
-extern "C" int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int kind, int bits, int channels, int64_t n_frames,
-                                   int in_rate, int16_t *out, int64_t out_capacity_frames, int64_t *n_out_frames) {
+static int resample_impl(blx_engine *e, const void *samples, bool storage16, int kind, int bits, int channels, int64_t n_frames,
+                         int in_rate, int16_t *out, int64_t out_capacity_frames, int64_t *n_out_frames) {
     int rc = check_engine(e);
     if (rc) return rc;
     if (!samples || !n_out_frames || n_frames <= 0 || (channels != 1 && channels != 2) || kind < 0 || kind > 3 || bits < 1 ||
@@ -859,7 +859,7 @@ extern "C" int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int ki
     if (!out) return BLX_OK; // size query
     if (out_capacity_frames < p.n_out) return fail(BLX_ERR_ARG, "output buffer too small");
     if (p.n_out == 0) return BLX_OK;
-    const size_t in_bytes = (size_t)n_frames * channels * 4, out_bytes = (size_t)p.n_out * 2 * 2;
+    const size_t in_bytes = (size_t)n_frames * channels * (storage16 ? 2 : 4), out_bytes = (size_t)p.n_out * 2 * 2;
     const size_t bank_bytes = bank_f.size() * 4 + bank_i.size() * 2;
     CK(e->scratch_a.reserve(in_bytes));
     CK(e->scratch_b.reserve(out_bytes + ((bank_bytes + 255) & ~(size_t)255) + 256));
@@ -869,7 +869,8 @@ extern "C" int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int ki
     if (bank_bytes)
         CK(cudaMemcpyAsync(d_bank, bank_f.empty() ? (const void *)bank_i.data() : (const void *)bank_f.data(), bank_bytes,
                            cudaMemcpyHostToDevice, st));
-    p.in = static_cast<const int *>(e->scratch_a.p);
+    p.in = storage16 ? nullptr : static_cast<const int *>(e->scratch_a.p);
+    p.in16 = storage16 ? static_cast<const short *>(e->scratch_a.p) : nullptr;
     p.out = static_cast<short *>(e->scratch_b.p);
     p.bank_f32 = reinterpret_cast<const float *>(d_bank);
     p.bank_s16 = reinterpret_cast<const short *>(d_bank);
@@ -878,6 +879,16 @@ extern "C" int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int ki
     CK(cudaMemcpyAsync(out, e->scratch_b.p, out_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return BLX_OK;
+}
+
+extern "C" int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int kind, int bits, int channels, int64_t n_frames,
+                                   int in_rate, int16_t *out, int64_t out_capacity_frames, int64_t *n_out_frames) {
+    return resample_impl(e, samples, false, kind, bits, channels, n_frames, in_rate, out, out_capacity_frames, n_out_frames);
+}
+
+extern "C" int blx_resample_s16_to_s16(blx_engine *e, const int16_t *samples, int channels, int64_t n_frames, int in_rate,
+                                       int16_t *out, int64_t out_capacity_frames, int64_t *n_out_frames) {
+    return resample_impl(e, samples, true, BLX_RS_KIND_S16, 16, channels, n_frames, in_rate, out, out_capacity_frames, n_out_frames);
 }
 
 // 44.1 kHz (or any-rate) mono / stereo float32 host buffers -> the decode-stage resampler on the device -> the native

@@ -69,6 +69,7 @@ cudaError_t launch_rect_filter(double *d_out, const double *d_in, int n, int wid
 // decode-stage resampler (include/blx_resample.h): in = the reader's int32 samples (interleaved), out = int16 stereo
 struct ResampleParams {
     const int *in;
+    const short *in16;      // non-null: the samples are stored as int16 (16-bit PCM files), `in` is unused
     short *out;
     const float *bank_f32;  // [P][L] (float-internal kinds)
     const short *bank_s16;  // [P][L] (BLX_RS_KIND_U8)

@@ -26,6 +26,8 @@ __device__ __forceinline__ float to_internal(int raw, int kind, int bits, bool m
     return v;
 }
 
+__device__ __forceinline__ int load_raw(const ResampleParams &p, long long i) { return p.in16 ? (int)p.in16[i] : p.in[i]; }
+
 __global__ void resample_kernel(ResampleParams p) {
     const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
@@ -33,7 +35,7 @@ __global__ void resample_kernel(ResampleParams p) {
     const bool mono = p.channels == 1;
     short v;
     if (p.P == 0) { // same rate: format conversion / up-mix only
-        const int raw = p.in[m * p.channels + (mono ? 0 : c)];
+        const int raw = load_raw(p, m * p.channels + (mono ? 0 : c));
         if (p.kind == BLX_RS_KIND_U8) {
             const int s16 = raw * 256;
             v = mono ? clip16((s16 * 23170 + 16384) >> 15) : (short)s16;
@@ -56,7 +58,7 @@ __global__ void resample_kernel(ResampleParams p) {
             for (int i = 0; i < p.L; ++i) {
                 const long long t = start + i;
                 const long long src = t < 0 ? -t : (t < p.n_in ? t : 2 * p.n_in - 1 - t);
-                int s16 = p.in[src * p.channels + c] * 256;
+                int s16 = load_raw(p, src * p.channels + c) * 256;
                 if (gain_first) s16 = clip16((s16 * 23170 + 16384) >> 15);
                 val += s16 * (int)h[i];
             }
@@ -72,7 +74,7 @@ __global__ void resample_kernel(ResampleParams p) {
                     if (i < p.L) {
                         const long long t = start + i;
                         const long long src = t < 0 ? -t : (t < p.n_in ? t : 2 * p.n_in - 1 - t);
-                        acc[j] = __fmaf_rn(to_internal(p.in[src * p.channels + c], p.kind, p.bits, gain_first), h[i], acc[j]);
+                        acc[j] = __fmaf_rn(to_internal(load_raw(p, src * p.channels + c), p.kind, p.bits, gain_first), h[i], acc[j]);
                     }
                 }
             }

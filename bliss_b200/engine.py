@@ -211,6 +211,19 @@ class Engine:
                                                    cnt.value, ctypes.byref(cnt)))
         return out
 
+    def resample_s16_to_s16(self, samples, channels, in_rate):
+        """The same for 16-bit sources stored as int16 (what bl_audio_decode uses for 16-bit WAVE files)."""
+        a = np.ascontiguousarray(samples, dtype=np.int16)
+        n = len(a) // channels
+        p = a.ctypes.data_as(L.c_i16p)
+        cnt = ctypes.c_int64(0)
+        self._ck(self._lib.blx_resample_s16_to_s16(self._h, p, channels, n, in_rate, None, 0, ctypes.byref(cnt)))
+        out = np.zeros(2 * cnt.value, dtype=np.int16)
+        if cnt.value:
+            self._ck(self._lib.blx_resample_s16_to_s16(self._h, p, channels, n, in_rate, out.ctypes.data_as(L.c_i16p), cnt.value,
+                                                       ctypes.byref(cnt)))
+        return out
+
     def envelope_energy(self, pcm):
         a = np.ascontiguousarray(pcm, dtype=np.int16)
         nb = 2 * (len(a) // 512)

@@ -70,15 +70,19 @@ int bl_audio_decode(char const *const filename, struct bl_song *const song) {
         /* everything else goes through the resampler (reference src/decode.c:313-345: libswresample to
          * int16 / 22 050 Hz / stereo; here include/blx_resample.h on the GPU) */
         const int kind = f.is_float ? BLX_RS_KIND_F32 : is_u8 ? BLX_RS_KIND_U8 : is_s16 ? BLX_RS_KIND_S16 : BLX_RS_KIND_S32;
-        blx_engine *e = blx_pcm_file_samples32(&f) == 0 ? bl_engine_acquire() : NULL;
+        /* 16-bit WAVE files arrive as int16 and go to the device as they are; everything else as the reader's int32 */
+        const int packed16 = f.samples16 != NULL && !f.samples;
+        blx_engine *e = (packed16 || blx_pcm_file_samples32(&f) == 0) ? bl_engine_acquire() : NULL;
         if (e) {
             int64_t n_out = 0;
-            int brc = blx_resample_to_s16(e, f.samples, kind, f.bits_per_sample, f.channels, (int64_t)f.n_frames, f.sample_rate,
-                                          NULL, 0, &n_out);
+            int brc = packed16 ? blx_resample_s16_to_s16(e, f.samples16, f.channels, (int64_t)f.n_frames, f.sample_rate, NULL, 0, &n_out)
+                               : blx_resample_to_s16(e, f.samples, kind, f.bits_per_sample, f.channels, (int64_t)f.n_frames,
+                                                     f.sample_rate, NULL, 0, &n_out);
             int16_t *pcm = NULL;
             if (brc == BLX_OK && n_out > 0 && n_out < ((int64_t)1 << 30)) pcm = (int16_t *)malloc((size_t)n_out * 2 * sizeof(int16_t));
-            if (pcm && blx_resample_to_s16(e, f.samples, kind, f.bits_per_sample, f.channels, (int64_t)f.n_frames, f.sample_rate,
-                                           pcm, n_out, &n_out) == BLX_OK) {
+            if (pcm && (packed16 ? blx_resample_s16_to_s16(e, f.samples16, f.channels, (int64_t)f.n_frames, f.sample_rate, pcm, n_out, &n_out)
+                                 : blx_resample_to_s16(e, f.samples, kind, f.bits_per_sample, f.channels, (int64_t)f.n_frames,
+                                                       f.sample_rate, pcm, n_out, &n_out)) == BLX_OK) {
                 song->sample_array = (int8_t *)pcm;
                 song->nSamples = (int)(2 * n_out);
                 song->resampled = 1;

@@ -202,6 +202,10 @@ int blx_frontend_f32(blx_engine *e, const float *pcm, int64_t n_in, int16_t *out
  * number of output frames. */
 int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int kind, int bits, int channels, int64_t n_frames,
                         int in_rate, int16_t *out, int64_t out_capacity_frames, int64_t *n_out_frames);
+/* The same for samples that are stored as int16 (16-bit PCM files, the CD-audio case): half the host->device bytes and
+ * no widening pass on the host. */
+int blx_resample_s16_to_s16(blx_engine *e, const int16_t *samples, int channels, int64_t n_frames, int in_rate, int16_t *out,
+                            int64_t out_capacity_frames, int64_t *n_out_frames);
 
 /* Envelope intermediates for kernel-level parity tests: hop energies E[m]
  * (reference src/tempo_atk_sort.c:150), 2 * (n_samples / 512) doubles, host. */

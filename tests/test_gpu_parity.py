@@ -96,7 +96,12 @@ def test_resampler_kernel_matches_oracle(engine, oracle):
     rng = np.random.default_rng(77)
     for rate, ch, n in ((48000, 2, 100003), (32000, 1, 50000), (12000, 2, 30000), (192000, 2, 90001), (7350, 1, 9000)):
         x = (rng.standard_normal(n * ch) * 7000).clip(-32768, 32767).astype(np.int32)
-        assert np.array_equal(engine.resample_to_s16(x, engine.RS_S16, 16, ch, rate), oracle.resample_to_s16(x, oracle.RS_S16, 16, ch, rate)), rate
+        ref = oracle.resample_to_s16(x, oracle.RS_S16, 16, ch, rate)
+        assert np.array_equal(engine.resample_to_s16(x, engine.RS_S16, 16, ch, rate), ref), rate
+        assert np.array_equal(engine.resample_s16_to_s16(x.astype(np.int16), ch, rate), ref), rate  # int16 storage, same result
+    for ch in (1, 2):  # same rate: up-mix / pass-through only
+        x = (rng.standard_normal(5000 * ch) * 7000).clip(-32768, 32767).astype(np.int32)
+        assert np.array_equal(engine.resample_s16_to_s16(x.astype(np.int16), ch, 22050), oracle.resample_to_s16(x, oracle.RS_S16, 16, ch, 22050))
     with pytest.raises(bliss_b200.BlxError):
         engine.resample_to_s16(np.zeros(4000, np.int32), engine.RS_S16, 16, 2, 47999)  # 22050 / 47999: more than 1024 phases
 

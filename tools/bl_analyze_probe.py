@@ -48,6 +48,14 @@ def main():
                 f.write(b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " +
                         struct.pack("<IHHIIHH", 16, 1, 2, 22050, 22050 * 4, 4, 16) + b"data" + struct.pack("<I", len(raw)) + raw)
             wavs.append(path.encode())
+        wav44 = []
+        for i in range(8):  # the most common real-world input: CD audio, 44.1 kHz 16-bit stereo -> resampler -> analysis
+            raw = (rng.standard_normal(2 * 180 * 44100) * 6000).astype(np.int16).tobytes()
+            path = os.path.join(d, f"c{i}.wav")
+            with open(path, "wb") as f:
+                f.write(b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " +
+                        struct.pack("<IHHIIHH", 16, 1, 2, 44100, 44100 * 4, 4, 16) + b"data" + struct.pack("<I", len(raw)) + raw)
+            wav44.append(path.encode())
         fixture = os.path.join(ROOT, "tests", "golden", "song.flac").encode()
         run(wavs, 16, 1)
         for rnd in range(3):
@@ -56,6 +64,8 @@ def main():
                 rec[f"wav_{th}"] = round(run(wavs, th, 4), 1)
             for th in (1, 8):
                 rec[f"fixture_{th}"] = round(run([fixture] * 16, th, 4), 1)
+            for th in (1, 8):
+                rec[f"wav44k_{th}"] = round(run(wav44, th, 2), 1)
             print(json.dumps(rec), flush=True)
 
 
