@@ -55,7 +55,7 @@ int bl_audio_decode(char const *const filename, struct bl_song *const song) {
         const size_t n = f.n_frames * (size_t)f.channels;
         const int shift = 16 - f.bits_per_sample;
         int16_t *pcm = NULL;
-        if (f.samples16) { /* 16-bit WAVE: the reader's buffer is the song's */
+        if (f.samples16) { /* 16-bit WAVE or FLAC: the reader's buffer is the song's */
             pcm = f.samples16;
             f.samples16 = NULL;
         } else if ((pcm = (int16_t *)malloc((n ? n : 1) * sizeof(int16_t))) != NULL) {
@@ -70,7 +70,7 @@ int bl_audio_decode(char const *const filename, struct bl_song *const song) {
         /* everything else goes through the resampler (reference src/decode.c:313-345: libswresample to
          * int16 / 22 050 Hz / stereo; here include/blx_resample.h on the GPU) */
         const int kind = f.is_float ? BLX_RS_KIND_F32 : is_u8 ? BLX_RS_KIND_U8 : is_s16 ? BLX_RS_KIND_S16 : BLX_RS_KIND_S32;
-        /* 16-bit WAVE files arrive as int16 and go to the device as they are; everything else as the reader's int32 */
+        /* 16-bit WAVE and FLAC files arrive as int16 and go to the device as they are; everything else as the reader's int32 */
         const int packed16 = f.samples16 != NULL && !f.samples;
         blx_engine *e = (packed16 || blx_pcm_file_samples32(&f) == 0) ? bl_engine_acquire() : NULL;
         if (e) {

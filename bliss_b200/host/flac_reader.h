@@ -6,7 +6,7 @@
 
 typedef struct blx_pcm_file {
     int32_t *samples;      /* interleaved, n_frames * channels; raw IEEE bits when is_float; NULL while only samples16 is held */
-    int16_t *samples16;    /* 16-bit PCM WAVE files are read straight into int16 (no widening pass); else NULL */
+    int16_t *samples16;    /* 16-bit WAVE and FLAC streams are delivered as int16 (no widening pass); else NULL */
     size_t n_frames;       /* sample frames (per channel) */
     int channels;
     int sample_rate;
