@@ -481,8 +481,9 @@ def chain_leg(torch, eng, E, dev, stream, rank, world, dist, barrier, max_over_r
 def bl_analyze_leg(torch, buf, stride, n_in, n_files=8):
     """songs/s through the reference's own entry point, bl_analyze(filename, &song) of include/bliss.h: file read + decode
     on the host, analysis on the GPU, per call; from 1 caller thread and from 8 (each call takes an engine out of the
-    library's pool, so concurrent callers overlap on the GPU). Files: the reference's 11-s fixture and 3-minute WAVs in
-    the analysers' native format (int16 / 22 050 Hz / stereo, written from the step's first songs)."""
+    library's pool, so concurrent callers overlap on the GPU). Files: the reference's 11-s fixture, 3-minute WAVs in
+    the analysers' native format (int16 / 22 050 Hz / stereo, written from the step's first songs) and 3-minute CD-audio
+    WAVs (44.1 kHz / 16 bit / stereo: through the decode-stage resampler)."""
     import struct
     import threading
 
@@ -501,6 +502,17 @@ def bl_analyze_leg(torch, buf, stride, n_in, n_files=8):
                 f.write(b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " +
                         struct.pack("<IHHIIHH", 16, 1, 2, 22050, 22050 * 4, 4, 16) + b"data" + struct.pack("<I", len(raw)) + raw)
             wavs.append(path.encode())
+        # the most common real-world input: CD audio (44.1 kHz / 16 bit / stereo) -> decode-stage resampler -> analysis
+        cd_wavs = []
+        for i in range(4):
+            mono = torch.clamp(torch.round(buf[i * stride:i * stride + n_in] * 32768.0), -32768, 32767).to(torch.int16)
+            pcm = torch.stack([mono, torch.roll(mono, 5)], dim=1).reshape(-1).cpu().numpy()
+            raw = pcm.tobytes()
+            path = os.path.join(d, f"cd{i}.wav")
+            with open(path, "wb") as f:
+                f.write(b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE" + b"fmt " +
+                        struct.pack("<IHHIIHH", 16, 1, 2, 44100, 44100 * 4, 4, 16) + b"data" + struct.pack("<I", len(raw)) + raw)
+            cd_wavs.append(path.encode())
         fixture = os.path.join(ROOT, "tests", "golden", "song.flac").encode()
 
         def run(files, threads, reps):
@@ -531,9 +543,13 @@ def bl_analyze_leg(torch, buf, stride, n_in, n_files=8):
         same = all(len(v) == 1 for v in r1.values()) and all(len(v) == 1 for v in r8.values()) and all(r1[k] == r8[k] for k in r1)
         fx1, _ = run([fixture] * 8, 1, 2)
         fx8, _ = run([fixture] * 8, 8, 4)
+        run(cd_wavs[:1], 1, 1)
+        cd1, _ = run(cd_wavs, 1, 2)
+        cd4, _ = run(cd_wavs, 4, 4)
         out = {"api": "bl_analyze (include/bliss.h), one file per call: host read + decode, GPU analysis",
                "wav_3min_songs_per_s_1_thread": one, "wav_3min_songs_per_s_8_threads": many,
                "fixture_11s_songs_per_s_1_thread": fx1, "fixture_11s_songs_per_s_8_threads": fx8,
+               "cd_wav_44k_3min_songs_per_s_1_thread": cd1, "cd_wav_44k_3min_songs_per_s_4_threads": cd4,
                "results_identical_across_threads": bool(same), "files": n_files}
     return out
 
