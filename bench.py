@@ -536,21 +536,32 @@ def bl_analyze_leg(torch, buf, stride, n_in, n_files=8):
             dt = time.perf_counter() - t0
             return len(files) * reps / dt, recs
 
+        def median_of(files, threads, reps, trials=3):
+            # calls of a few milliseconds from several threads are at the mercy of the host's allocator and scheduler:
+            # the median of three short trials is reported, results of all of them are kept for the identity check
+            rates, recs = [], {}
+            for _ in range(trials):
+                r, rc = run(files, threads, reps)
+                rates.append(r)
+                for k, v in rc.items():
+                    recs.setdefault(k, set()).update(v)
+            return sorted(rates)[len(rates) // 2], recs
+
         run(wavs[:2], 1, 1)  # warm-up: engine pool, kernel attributes
         run(wavs, 8, 1)
-        one, r1 = run(wavs, 1, 2)
-        many, r8 = run(wavs, 8, 4)
+        one, r1 = median_of(wavs, 1, 1)
+        many, r8 = median_of(wavs, 8, 4)
         same = all(len(v) == 1 for v in r1.values()) and all(len(v) == 1 for v in r8.values()) and all(r1[k] == r8[k] for k in r1)
-        fx1, _ = run([fixture] * 8, 1, 2)
-        fx8, _ = run([fixture] * 8, 8, 4)
+        fx1, _ = median_of([fixture] * 8, 1, 2)
+        fx8, _ = median_of([fixture] * 8, 8, 4)
         run(cd_wavs[:1], 1, 1)
-        cd1, _ = run(cd_wavs, 1, 2)
-        cd4, _ = run(cd_wavs, 4, 4)
+        cd1, _ = median_of(cd_wavs, 1, 1)
+        cd4, _ = median_of(cd_wavs, 4, 2)
         out = {"api": "bl_analyze (include/bliss.h), one file per call: host read + decode, GPU analysis",
                "wav_3min_songs_per_s_1_thread": one, "wav_3min_songs_per_s_8_threads": many,
                "fixture_11s_songs_per_s_1_thread": fx1, "fixture_11s_songs_per_s_8_threads": fx8,
                "cd_wav_44k_3min_songs_per_s_1_thread": cd1, "cd_wav_44k_3min_songs_per_s_4_threads": cd4,
-               "results_identical_across_threads": bool(same), "files": n_files}
+               "results_identical_across_threads": bool(same), "files": n_files, "statistic": "median of 3 trials"}
     return out
 
 
