@@ -29,6 +29,11 @@ int bl_audio_decode(char const *const filename, struct bl_song *const song) {
         fprintf(stderr, "Couldn't open file: %s (not a readable FLAC or WAV file)\n", filename);
         return BL_UNEXPECTED;
     }
+    if (f.sample_rate <= 0 || f.n_frames == 0 || f.n_frames > (size_t)0x3fffffff) { /* nSamples is an int (bliss.h) */
+        fprintf(stderr, "Couldn't decode %s: unusable stream parameters (%d Hz, %zu frames)\n", filename, f.sample_rate, f.n_frames);
+        blx_pcm_file_free(&f);
+        return BL_UNEXPECTED;
+    }
     const double seconds = (double)f.n_frames / (double)f.sample_rate;
     song->filename = dup_or(filename, "");
     song->duration = (uint64_t)seconds;                       /* reference src/decode.c:235 */

@@ -92,6 +92,9 @@ def test_decode_error_paths(tmp_path, capfd):
     write_wav(tmp_path / "six.wav", six, 22050, 6, 1, 16)  # 5.1: no down-mix matrix in this build
     assert decode(tmp_path / "six.wav")[2] == -2
     assert "down-mix" in capfd.readouterr().err
+    write_wav(tmp_path / "rate0.wav", np.zeros(2000, dtype=np.int16), 0, 2, 1, 16)  # a header that claims 0 Hz
+    assert decode(tmp_path / "rate0.wav")[2] == -2
+    assert "unusable stream parameters" in capfd.readouterr().err
     assert L.bl_analyze(str(tmp_path / "missing.flac").encode(), ctypes.byref(bliss_b200.BlSong())) == -2
 
 
