@@ -126,6 +126,35 @@ def test_files_at_other_rates_and_formats_go_through_the_resampler(tmp_path, ora
         L.bl_free_song(ctypes.byref(s))
 
 
+@pytest.mark.gpu
+def test_cd_audio_flac_goes_through_the_resampler(tmp_path, oracle):
+    """The everyday input: 44.1 kHz / 16 bit / stereo FLAC (here from the test encoder; large enough for the threaded
+    decoder). Decoded straight to int16, resampled on the GPU as int16, analysed: PCM equal to the oracle resampler's, force
+    vector equal to the reference analysers' on that PCM. A 12-bit mono FLAC at 32 kHz takes the int32 route."""
+    from flac_encode import encode
+    x = song_f32(11, 6.0)
+    xs = np.round(np.stack([x * 0.9, np.roll(x, 23) * 0.6], axis=1) * 32767).astype(np.int64)
+    plan = lambda fi: dict(kind=["lpc", "fixed2", "fixed4"][fi % 3], stereo=[None, 8, 9, 10][fi % 4], lpc_order=1 + (fi * 3) % 12, porder=3)
+    (tmp_path / "cd.flac").write_bytes(encode(xs, 16, 44100, 4096, plan, seed=3))
+    L, s, rc = decode(tmp_path / "cd.flac")
+    assert rc == 0 and s.resampled == 1 and s.channels == 2 and s.sample_rate == 22050 and s.duration == 6
+    want = oracle.resample_to_s16(xs.astype(np.int32).reshape(-1), oracle.RS_S16, 16, 2, 44100)
+    assert np.array_equal(pcm_of(s), want)
+    L.bl_free_song(ctypes.byref(s))
+    s2 = bliss_b200.BlSong()
+    assert L.bl_analyze(str(tmp_path / "cd.flac").encode(), ctypes.byref(s2)) in (0, 1)
+    ref = oracle.analyze(want, 6)
+    for k in ("tempo", "amplitude", "frequency", "attack"):
+        assert abs(getattr(s2.force_vector, k) - ref[k]) <= 1e-4 * max(abs(ref[k]), 1e-30), k
+    L.bl_free_song(ctypes.byref(s2))
+    m = np.round(song_f32(12, 2.0)[:60000] * 2047).astype(np.int64).reshape(-1, 1)
+    (tmp_path / "m12.flac").write_bytes(encode(m, 12, 32000, 1024, lambda fi: dict(kind="lpc", lpc_order=6), seed=4))
+    L, s, rc = decode(tmp_path / "m12.flac")
+    assert rc == 0 and s.resampled == 1
+    assert np.array_equal(pcm_of(s), oracle.resample_to_s16(m.astype(np.int32).reshape(-1), oracle.RS_S16, 12, 1, 32000))
+    L.bl_free_song(ctypes.byref(s))
+
+
 def test_flac_frame_checksums_reject_damaged_frames(tmp_path):
     """A FLAC frame whose CRC-16 (or header CRC-8) does not match is dropped, not decoded as audio, and a sync code that
     happens to occur inside foreign bytes is not taken for a frame: the rest of the file decodes bit for bit."""
