@@ -891,6 +891,44 @@ extern "C" int blx_resample_s16_to_s16(blx_engine *e, const int16_t *samples, in
     return resample_impl(e, samples, true, BLX_RS_KIND_S16, 16, channels, n_frames, in_rate, out, out_capacity_frames, n_out_frames);
 }
 
+// FLAC frames on the device (flacdec.cu). `hdr` is the host reader's chain of frames (flac_hdr[n_frames], 40 bytes each,
+// host/flac_core.h), `first` the first sample of every frame; out receives samples * channels interleaved int16 (out16)
+// or int32 values. BLX_ERR_ARG with "frame" in the message = a frame did not check out: decode on the host instead.
+extern "C" int blx_flac_decode_frames(blx_engine *e, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first,
+                                      int n_frames, int channels, int out16, uint64_t samples, void *out) {
+    int rc = check_engine(e);
+    if (rc) return rc;
+    if (!file || !hdr || !first || !out || n_frames <= 0 || channels < 1 || channels > 8 || samples == 0 || samples > ((uint64_t)1 << 32))
+        return fail(BLX_ERR_ARG, "bad FLAC decode arguments");
+    const size_t hdr_bytes = (size_t)n_frames * 40, first_bytes = (size_t)n_frames * 8;
+    const size_t o_hdr = (n_bytes + 255) & ~(size_t)255, o_first = o_hdr + ((hdr_bytes + 255) & ~(size_t)255);
+    const size_t o_fail = o_first + ((first_bytes + 255) & ~(size_t)255);
+    const size_t scratch_bytes = (size_t)samples * channels * 4, out_bytes = (size_t)samples * channels * (out16 ? 2 : 4);
+    CK(e->scratch_a.reserve(o_fail + 256));
+    CK(e->scratch_b.reserve(((scratch_bytes + 255) & ~(size_t)255) + out_bytes));
+    cudaStream_t st = e->compute;
+    unsigned char *a = static_cast<unsigned char *>(e->scratch_a.p), *b = static_cast<unsigned char *>(e->scratch_b.p);
+    CK(cudaMemcpyAsync(a, file, n_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(a + o_hdr, hdr, hdr_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(a + o_first, first, first_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(a + o_fail, 0, 4, st));
+    FlacDecodeParams p;
+    p.data = a; p.n_bytes = n_bytes; p.hdr = a + o_hdr;
+    p.first = reinterpret_cast<const unsigned long long *>(a + o_first);
+    p.n_frames = n_frames; p.channels = channels; p.out16 = out16;
+    p.scratch = reinterpret_cast<int *>(b);
+    p.out = b + ((scratch_bytes + 255) & ~(size_t)255);
+    p.fail = reinterpret_cast<int *>(a + o_fail);
+    e->launches++;
+    CK(launch_flac_decode(p, st));
+    int failed = 0;
+    CK(cudaMemcpyAsync(&failed, p.fail, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out, p.out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (failed) return fail(BLX_ERR_ARG, "a FLAC frame did not decode on the device (damaged stream or a false frame boundary)");
+    return BLX_OK;
+}
+
 // 44.1 kHz (or any-rate) mono / stereo float32 host buffers -> the decode-stage resampler on the device -> the native
 // int16 pipeline: what bl_analyze computes for a float file, for callers that hold the decoded float PCM themselves.
 extern "C" int blx_analyze_batch_f32_exact(blx_engine *e, const float *const *pcm, const int64_t *n_frames, int channels, int in_rate,

@@ -79,6 +79,21 @@ struct ResampleParams {
     int mono_gain_last;     // BLX_RS_MONO_GAIN_LAST(in_rate)
 };
 cudaError_t launch_resample(const ResampleParams &p, cudaStream_t st);
+
+// FLAC frames on the device (flacdec.cu): one thread per frame of the chain the host found
+struct FlacDecodeParams {
+    const unsigned char *data;            // the file
+    size_t n_bytes;
+    const void *hdr;                      // flac_hdr[n_frames] (host/flac_core.h)
+    const unsigned long long *first;      // first sample (per channel) of every frame
+    int n_frames, channels, out16;
+    int *scratch;                         // planar per frame, samples * channels ints
+    void *out;                            // interleaved int16 (out16) or int32
+    int *fail;                            // set to 1 by any frame that does not check out
+};
+cudaError_t launch_flac_decode(const FlacDecodeParams &p, cudaStream_t st);
+void h_crc16_tab_set(int i);
+bool flac_decode_on_host(const FlacDecodeParams &p); // the host instance of the same code (tests)
 cudaError_t launch_dfma_peak(double *d_scratch, int blocks, int threads, int iters, cudaStream_t st);
 cudaError_t launch_frontend(const float *d_in, long long n_in, short *d_out, cudaStream_t st);
 

@@ -22,6 +22,36 @@ static char *dup_or(const char *s, const char *fallback) {
     return d;
 }
 
+int blx_flac_decode_frames_emulated(const unsigned char *file, size_t n_bytes, const void *hdr, const unsigned long long *first,
+                                    int n_frames, int channels, int out16, unsigned long long samples, void *out);
+
+/* Long FLAC streams are decoded on the device (csrc/flacdec.cu): the reader calls back with the chain of frames it found. */
+static int g_flac_accel_ok = 0; /* streams the accelerator decoded (diagnostic; tests assert that it ran) */
+int blx_flac_accelerated_count(void) { return __atomic_load_n(&g_flac_accel_ok, __ATOMIC_RELAXED); }
+
+static int flac_on_device_impl(const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames, int channels,
+                               int out16, uint64_t samples, void *out);
+static int flac_on_device(const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames, int channels,
+                          int out16, uint64_t samples, void *out) {
+    const int rc = flac_on_device_impl(file, n_bytes, hdr, first, n_frames, channels, out16, samples, out);
+    if (rc == 0) __atomic_add_fetch(&g_flac_accel_ok, 1, __ATOMIC_RELAXED);
+    return rc;
+}
+
+static int flac_on_device_impl(const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames, int channels,
+                          int out16, uint64_t samples, void *out) {
+    if (n_frames > 0x7fffffff) return -1;
+    if (getenv("BLX_FLAC_EMULATE")) /* tests without a GPU: the host instance of the device code */
+        return blx_flac_decode_frames_emulated(file, n_bytes, hdr, (const unsigned long long *)first, (int)n_frames, channels, out16,
+                                               samples, out);
+    blx_engine *e = bl_engine_acquire();
+    if (!e) return -1;
+    const int rc = blx_flac_decode_frames(e, file, n_bytes, hdr, first, (int)n_frames, channels, out16, samples, out);
+    bl_engine_release();
+    return rc == BLX_OK ? 0 : -1;
+}
+__attribute__((constructor)) static void install_flac_accel(void) { blx_flac_accel = flac_on_device; }
+
 int bl_audio_decode(char const *const filename, struct bl_song *const song) {
     blx_pcm_file f;
     bl_initialize_song(song);

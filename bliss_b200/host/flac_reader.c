@@ -20,87 +20,6 @@
 #include <strings.h>
 
 /* ------------------------------------------------------------------ */
-/* bit reader                                                          */
-/* ------------------------------------------------------------------ */
-typedef struct {
-    const uint8_t *p;
-    size_t n;
-    size_t pos;   /* next byte to load (runs past n at the end of the data: zeros are shifted in) */
-    uint64_t acc; /* bit window, MSB first: the next bit of the stream is bit 63; bits below the valid `cnt` are 0 */
-    int cnt;      /* valid bits in acc */
-} bitrd;
-
-static void br_init(bitrd *b, const uint8_t *p, size_t n, size_t pos) {
-    b->p = p; b->n = n; b->pos = pos; b->acc = 0; b->cnt = 0;
-}
-
-/* Tops the window up to at least 57 valid bits: one unaligned 8-byte load when the data allows, byte by byte at its end. */
-static inline void br_refill(bitrd *b) {
-    if (b->pos + 8 <= b->n) {
-        uint64_t w;
-        memcpy(&w, b->p + b->pos, 8);
-        w = __builtin_bswap64(w); /* little-endian host (as everywhere in this library) */
-        b->acc |= w >> b->cnt;
-        const int take = (63 - b->cnt) >> 3; /* whole bytes that fit */
-        b->pos += (size_t)take;
-        b->cnt += take * 8;
-        b->acc &= ~(~0ull >> b->cnt); /* the bits of the partly loaded next byte stay out of the window (56 <= cnt <= 63) */
-        return;
-    }
-    while (b->cnt <= 56) {
-        const uint64_t byte = (b->pos < b->n) ? b->p[b->pos] : 0;
-        b->pos++;
-        b->acc |= byte << (56 - b->cnt);
-        b->cnt += 8;
-    }
-}
-
-/* bytes of the stream consumed so far; more than n = the reader ran off the end of the data */
-static inline size_t br_bytepos(const bitrd *b) { return b->pos - (size_t)(b->cnt >> 3); }
-static inline int br_err(const bitrd *b) { return br_bytepos(b) > b->n; }
-
-static inline uint32_t br_u(bitrd *b, int nbits) { /* nbits <= 32 */
-    if (nbits == 0) return 0;
-    if (b->cnt < nbits) br_refill(b);
-    const uint32_t v = (uint32_t)(b->acc >> (64 - nbits));
-    b->acc <<= nbits;
-    b->cnt -= nbits;
-    return v;
-}
-
-static inline int32_t br_s(bitrd *b, int nbits) {
-    uint32_t v = br_u(b, nbits);
-    if (nbits == 0) return 0;
-    if (nbits < 32 && (v >> (nbits - 1))) v |= ~((1u << nbits) - 1u);
-    return (int32_t)v;
-}
-
-static inline uint32_t br_unary(bitrd *b) { /* count zeros before the next 1 bit */
-    uint32_t z = 0;
-    for (;;) {
-        if (b->acc == 0) { /* only zeros in the window */
-            z += (uint32_t)b->cnt;
-            b->cnt = 0;
-            if (b->pos >= b->n + 8) return z; /* nothing but the padding behind the data: the caller sees br_err */
-            br_refill(b);
-            continue;
-        }
-        const int lz = __builtin_clzll(b->acc); /* < cnt: the bits below cnt are zero */
-        z += (uint32_t)lz;
-        b->acc <<= lz;   /* two shifts: lz + 1 may be 64 */
-        b->acc <<= 1;
-        b->cnt -= lz + 1;
-        return z;
-    }
-}
-
-static inline void br_align(bitrd *b) {
-    const int drop = b->cnt & 7;
-    b->acc <<= drop;
-    b->cnt -= drop;
-}
-
-/* ------------------------------------------------------------------ */
 /* FLAC                                                                */
 /* ------------------------------------------------------------------ */
 /* Frame checksums (RFC 9639 section 9.1.8 / 9.3): CRC-8 of the header (polynomial x^8 + x^2 + x + 1) and CRC-16 of
@@ -141,56 +60,11 @@ static uint16_t crc16_of(const uint8_t *p, size_t n) {
     return c;
 }
 
-#ifndef BLX_RICE_FAST
-#define BLX_RICE_FAST 1
-#endif
-static int read_residual(bitrd *b, int32_t *out, int blocksize, int pred_order) {
-    int method = (int)br_u(b, 2);
-    if (method > 1) return -1;
-    int pbits = method ? 5 : 4;
-    uint32_t escape = method ? 31u : 15u;
-    int porder = (int)br_u(b, 4);
-    int nparts = 1 << porder;
-    if ((blocksize >> porder) << porder != blocksize && porder > 0) return -1;
-    int idx = pred_order;
-    for (int part = 0; part < nparts; ++part) {
-        int count = (blocksize >> porder) - (part == 0 ? pred_order : 0);
-        if (count < 0) return -1;
-        uint32_t param = br_u(b, pbits);
-        if (param == escape) {
-            int raw = (int)br_u(b, 5);
-            for (int i = 0; i < count; ++i) out[idx++] = br_s(b, raw);
-        } else {
-            for (int i = 0; i < count; ++i) {
-                uint32_t u;
-                if (b->cnt < 57) br_refill(b);
-                if (BLX_RICE_FAST && param <= 16 && (b->acc >> 24) != 0) {
-                    /* the usual case in one go: fewer than 40 zeros, the stop bit and the low bits all sit in the window */
-                    const int lz = __builtin_clzll(b->acc);
-                    const uint64_t rest = b->acc << lz << 1;
-                    const uint32_t r = (uint32_t)((rest >> 32) >> (32 - param)); /* param = 0: a 32-bit word shifted out whole */
-                    u = ((uint32_t)lz << param) | (param ? r : 0u);
-                    b->acc = rest << param;
-                    b->cnt -= lz + 1 + (int)param;
-                } else {
-                    const uint32_t q = br_unary(b);
-                    const uint32_t r = br_u(b, (int)param);
-                    u = (q << param) | r;
-                }
-                out[idx++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-            }
-        }
-        if (br_err(b)) return -1;
-    }
-    return 0;
-}
-
 /* LPC synthesis out[i] += (sum_j coef[j] out[i - 1 - j]) >> shift, i = order..n-1 (RFC 9639 section 9.2.6), the inner
  * loop of the decoder: the taps are reversed once so that the dot product runs over contiguous samples, the common
  * orders get a loop with a constant trip count (unrolled and vectorised by the compiler; an AVX2 clone is picked at
  * load time where the CPU has it), and 32-bit accumulators are used when bps + precision + log2(order) <= 32 bits
  * guarantees that nothing overflows them. */
-static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 /* (the 32-bit form works on unsigned words, so a damaged file whose samples outgrow their declared width wraps around
  * instead of running into signed overflow) */
@@ -225,54 +99,9 @@ BLX_CLONES static void lpc_restore(int32_t *out, int n, int order, const int32_t
     else { BLX_LPC_SWITCH(int64_t) }
 }
 
-static int read_subframe(bitrd *b, int32_t *out, int blocksize, int bps) {
-    if (br_u(b, 1)) return -1; /* padding */
-    int type = (int)br_u(b, 6);
-    int wasted = 0;
-    if (br_u(b, 1)) wasted = (int)br_unary(b) + 1;
-    bps -= wasted;
-    /* samples are kept in int32: the 33-bit side channel of a 32-bit stereo stream is not supported */
-    if (bps <= 0 || bps > 32) return -1;
-    if (type == 0) { /* constant */
-        int32_t v = br_s(b, bps);
-        for (int i = 0; i < blocksize; ++i) out[i] = v;
-    } else if (type == 1) { /* verbatim */
-        for (int i = 0; i < blocksize; ++i) out[i] = br_s(b, bps);
-    } else if (type >= 8 && type <= 12) { /* fixed predictor */
-        int order = type - 8;
-        if (order > blocksize) return -1;
-        for (int i = 0; i < order; ++i) out[i] = br_s(b, bps);
-        if (read_residual(b, out, blocksize, order)) return -1;
-        for (int i = order; i < blocksize; ++i) {
-            int64_t p = 0;
-            switch (order) {
-                case 1: p = out[i - 1]; break;
-                case 2: p = 2 * (int64_t)out[i - 1] - out[i - 2]; break;
-                case 3: p = 3 * (int64_t)out[i - 1] - 3 * (int64_t)out[i - 2] + out[i - 3]; break;
-                case 4: p = 4 * (int64_t)out[i - 1] - 6 * (int64_t)out[i - 2] + 4 * (int64_t)out[i - 3] - out[i - 4]; break;
-                default: break;
-            }
-            out[i] = (int32_t)(p + out[i]);
-        }
-    } else if (type >= 32) { /* LPC */
-        int order = type - 31;
-        if (order > blocksize) return -1;
-        int32_t coef[32];
-        for (int i = 0; i < order; ++i) out[i] = br_s(b, bps);
-        int prec = (int)br_u(b, 4) + 1;
-        if (prec == 16) return -1;
-        int shift = br_s(b, 5);
-        if (shift < 0) return -1;
-        for (int i = 0; i < order; ++i) coef[i] = br_s(b, prec);
-        if (read_residual(b, out, blocksize, order)) return -1;
-        lpc_restore(out, blocksize, order, coef, shift, bps + prec + ilog2_ceil(order) <= 32);
-    } else {
-        return -1;
-    }
-    if (wasted)
-        for (int i = 0; i < blocksize; ++i) out[i] = (int32_t)((uint32_t)out[i] << wasted);
-    return br_err(b) ? -1 : 0;
-}
+#define FLAC_LPC lpc_restore
+#define FLAC_CRC16 crc16_of
+#include "flac_core.h"
 
 static void add_tag(blx_pcm_file *f, const char *kv, size_t len) {
     const char *eq = memchr(kv, '=', len);
@@ -292,14 +121,6 @@ static void add_tag(blx_pcm_file *f, const char *kv, size_t len) {
 }
 
 /* ---- frames ---------------------------------------------------------------------------------------------------- */
-typedef struct {
-    size_t off;        /* byte offset of the sync code */
-    size_t hdr_len;    /* header bytes incl. CRC-8 */
-    int blocksize, ch_code, bps;
-    int variable;      /* blocking strategy bit: the coded number counts samples, not frames */
-    uint64_t number;   /* coded frame / sample number */
-} flac_hdr;
-
 /* Parses and checks (CRC-8, channel count) the frame header at d[pos]; 0 if there is a plausible one. */
 static int parse_frame_header(const uint8_t *d, size_t n, size_t pos, const blx_pcm_file *f, flac_hdr *h) {
     if (pos + 6 > n || d[pos] != 0xFF || (d[pos + 1] & 0xFE) != 0xF8) return -1;
@@ -344,36 +165,6 @@ static int parse_frame_header(const uint8_t *d, size_t n, size_t pos, const blx_
     return 0;
 }
 
-/* Decodes the frame whose (checked) header is h into chbuf (channel c at chbuf + c * 65536), stereo decorrelation
- * undone; *end = the byte behind its CRC-16. 0 = good frame, 1 = damaged (resynchronise), -1 = ran off the data. */
-static int decode_frame(const uint8_t *d, size_t n, const flac_hdr *h, int32_t *chbuf, size_t *end) {
-    bitrd b;
-    br_init(&b, d, n, h->off + h->hdr_len);
-    const int nch = (h->ch_code < 8) ? h->ch_code + 1 : 2, blocksize = h->blocksize;
-    for (int c = 0; c < nch; ++c) {
-        const int side = (h->ch_code == 8 && c == 1) || (h->ch_code == 9 && c == 0) || (h->ch_code == 10 && c == 1);
-        if (read_subframe(&b, chbuf + (size_t)c * 65536, blocksize, h->bps + side)) return 1;
-    }
-    br_align(&b);
-    const size_t body_end = br_bytepos(&b);
-    const uint32_t crc16 = br_u(&b, 16);
-    if (br_err(&b)) return -1;
-    if (crc16 != crc16_of(d + h->off, body_end - h->off)) return 1;
-    int32_t *c0 = chbuf, *c1 = chbuf + 65536;
-    if (h->ch_code == 8) { for (int i = 0; i < blocksize; ++i) c1[i] = c0[i] - c1[i]; }
-    else if (h->ch_code == 9) { for (int i = 0; i < blocksize; ++i) c0[i] = c0[i] + c1[i]; }
-    else if (h->ch_code == 10) {
-        for (int i = 0; i < blocksize; ++i) {
-            const int32_t side = c1[i];
-            const int32_t mid = (int32_t)(((uint32_t)c0[i] << 1) | (uint32_t)(side & 1));
-            c0[i] = (mid + side) >> 1;
-            c1[i] = (mid - side) >> 1;
-        }
-    }
-    *end = br_bytepos(&b);
-    return 0;
-}
-
 /* 16-bit streams are delivered as int16 (blx_pcm_file.samples16): half the memory traffic on the host and on the way
  * to the device */
 static void interleave16(int16_t *dst, const int32_t *chbuf, int blocksize, int nch) {
@@ -394,6 +185,8 @@ static void interleave(int32_t *dst, const int32_t *chbuf, int blocksize, int nc
             for (int c = 0; c < nch; ++c) dst[(size_t)i * (size_t)nch + (size_t)c] = chbuf[(size_t)c * 65536 + (size_t)i];
     }
 }
+
+blx_flac_accel_fn blx_flac_accel = NULL;
 
 /* ---- parallel decode: the frames of a stream are independent ------------------------------------------------------ */
 typedef struct {
@@ -426,7 +219,7 @@ static void *flac_worker(void *arg) {
         for (size_t k = lo; k < hi; ++k) {
             size_t end = 0;
             const size_t want = (k + 1 < j->n_frames) ? j->hdr[k + 1].off : 0;
-            if (decode_frame(j->d, j->n, &j->hdr[k], chbuf, &end) != 0 || (want && end != want)) {
+            if (decode_frame(j->d, j->n, &j->hdr[k], chbuf, 65536, &end) != 0 || (want && end != want)) {
                 pthread_mutex_lock(&j->lock);
                 j->failed = 1;
                 pthread_mutex_unlock(&j->lock);
@@ -489,6 +282,22 @@ static int decode_flac_parallel(const uint8_t *d, size_t n, size_t pos, uint64_t
         job.out16 = f->bits_per_sample == 16;
         job.pcm = malloc(samples * (size_t)f->channels * (job.out16 ? sizeof(int16_t) : sizeof(int32_t)));
         if (!job.pcm) goto out;
+        /* long streams: the device decoder, if the library provides one (BLX_FLAC_GPU=0 turns it off) */
+        {
+            const char *sw = getenv("BLX_FLAC_GPU"), *mn = getenv("BLX_FLAC_GPU_MIN_SAMPLES");
+            const unsigned long long min_samples = mn ? strtoull(mn, NULL, 10) : 4000000ull; /* ~45 s of CD audio */
+            if (blx_flac_accel && !(sw && sw[0] == '0') && (unsigned long long)samples * (unsigned)f->channels >= min_samples &&
+                sizeof(size_t) == sizeof(uint64_t) &&
+                blx_flac_accel(d, n, hdr, (const uint64_t *)first, nf, f->channels, job.out16, (uint64_t)samples, job.pcm) == 0) {
+                size_t nframes = samples;
+                if (total && nframes > total) nframes = (size_t)total;
+                if (job.out16) f->samples16 = (int16_t *)job.pcm;
+                else f->samples = (int32_t *)job.pcm;
+                f->n_frames = nframes;
+                rc = 0;
+                goto out;
+            }
+        }
         pthread_mutex_init(&job.lock, NULL);
         pthread_t th[32];
         int started = 0;
@@ -533,7 +342,7 @@ static int decode_flac_frames(const uint8_t *d, size_t n, size_t pos, uint64_t t
         flac_hdr h;
         if (parse_frame_header(d, n, pos, f, &h) != 0) { pos++; continue; }
         size_t end = 0;
-        const int fr = decode_frame(d, n, &h, chbuf, &end);
+        const int fr = decode_frame(d, n, &h, chbuf, 65536, &end);
         if (fr < 0) break;
         if (fr > 0) { pos++; continue; } /* damaged frame: resynchronise */
         if (nframes + (size_t)h.blocksize > cap) {

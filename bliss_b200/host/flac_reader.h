@@ -18,6 +18,14 @@ typedef struct blx_pcm_file {
     char *artist, *title, *album, *tracknumber, *genre; /* NULL when absent */
 } blx_pcm_file;
 
+/* Optional accelerator for long FLAC streams: the library (decode.c) points it at the device decoder (one thread per frame,
+ * csrc/flacdec.cu); NULL in stand-alone builds of the reader (tools, fuzzer). It gets the file, the chain of frames the
+ * scan found (flac_hdr records, flac_core.h) and the first sample of each, and fills `out` (interleaved int16 if out16,
+ * else int32); anything but 0 makes the reader decode on the host threads instead. */
+typedef int (*blx_flac_accel_fn)(const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames,
+                                 int channels, int out16, uint64_t samples, void *out);
+extern blx_flac_accel_fn blx_flac_accel;
+
 int blx_pcm_file_read(const char *filename, blx_pcm_file *out); /* 0 on success */
 int blx_pcm_file_samples32(blx_pcm_file *f); /* makes f->samples valid (widens samples16 if need be); 0 on success */
 void blx_pcm_file_free(blx_pcm_file *f);

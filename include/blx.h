@@ -207,6 +207,17 @@ int blx_resample_to_s16(blx_engine *e, const int32_t *samples, int kind, int bit
 int blx_resample_s16_to_s16(blx_engine *e, const int16_t *samples, int channels, int64_t n_frames, int in_rate, int16_t *out,
                             int64_t out_capacity_frames, int64_t *n_out_frames);
 
+/* FLAC frames decoded on the device, one thread per frame (csrc/flacdec.cu; the decode stage of reference
+ * src/decode.c:352-427 for FLAC input). `hdr` = the chain of frames the host reader found (n_frames records of 40 bytes,
+ * bliss_b200/host/flac_core.h), `first` = the first sample of every frame, `out` = samples * channels interleaved int16
+ * (out16 != 0, 16-bit streams) or int32 values on the host. Fails (BLX_ERR_ARG) if any frame does not pass its CRC-16 or
+ * does not end where the next begins: the caller then decodes on the host, which resynchronises. */
+int blx_flac_decode_frames(blx_engine *e, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, int n_frames,
+                           int channels, int out16, uint64_t samples, void *out);
+
+/* Diagnostic: how many FLAC streams bl_audio_decode has decoded through the device decoder so far in this process. */
+int blx_flac_accelerated_count(void);
+
 /* Envelope intermediates for kernel-level parity tests: hop energies E[m]
  * (reference src/tempo_atk_sort.c:150), 2 * (n_samples / 512) doubles, host. */
 int blx_envelope_energy_s16(blx_engine *e, const int16_t *pcm, int n_samples, double *energy);

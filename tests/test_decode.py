@@ -155,6 +155,53 @@ def test_cd_audio_flac_goes_through_the_resampler(tmp_path, oracle):
     L.bl_free_song(ctypes.byref(s))
 
 
+@pytest.mark.gpu
+def test_flac_frames_decode_on_the_device(tmp_path, monkeypatch):
+    """Long FLAC streams are decoded on the GPU, one thread per frame (csrc/flacdec.cu): same samples as the host decoder
+    for the reference's fixtures (forced onto the device path), a three-minute stream and encoder streams with every
+    subframe type; a damaged stream is refused by the device and decoded by the host fall-back."""
+    from flac_encode import encode
+    from flac_util import read_pcm_file, repeat_flac
+    L = bliss_b200.load()
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    files = [os.path.join(golden, n) for n in ("song.flac", "song_s32.flac", "song_s32_mono.flac")]
+    (tmp_path / "long.flac").write_bytes(repeat_flac(files[0], 16))  # 177 s, above the default threshold
+    files.append(str(tmp_path / "long.flac"))
+    rng = np.random.default_rng(5)
+    t = np.arange(1152 * 120)
+    pcm = np.stack([8000 * np.sin(t / 37.0) + rng.standard_normal(len(t)) * 900, 6000 * np.sin(t / 41.0) + rng.standard_normal(len(t)) * 900],
+                   axis=1).round().astype(np.int64)
+    kinds = ["lpc", "fixed0", "fixed1", "fixed2", "fixed3", "fixed4", "verbatim"]
+    plan = lambda fi: dict(kind=kinds[fi % 7], stereo=[None, 8, 9, 10][fi % 4], lpc_order=1 + (fi * 5) % 32, method=fi % 2,
+                           porder=[0, 1, 3, 5][fi % 4], escape_parts=(0,) if fi % 6 == 5 else ())
+    (tmp_path / "enc16.flac").write_bytes(encode(pcm, 16, 44100, 1152, plan, seed=1))
+    (tmp_path / "enc24.flac").write_bytes(encode(pcm * 200, 24, 48000, 1152, plan, seed=2))
+    files += [str(tmp_path / "enc16.flac"), str(tmp_path / "enc24.flac")]
+    blob = bytearray(open(files[3], "rb").read())
+    blob[len(blob) // 3] ^= 0x10
+    (tmp_path / "damaged.flac").write_bytes(bytes(blob))
+    files.append(str(tmp_path / "damaged.flac"))
+    monkeypatch.delenv("BLX_FLAC_EMULATE", raising=False)
+    for path in files:
+        monkeypatch.setenv("BLX_FLAC_GPU", "0")
+        ref = read_pcm_file(path)
+        monkeypatch.setenv("BLX_FLAC_GPU", "1")
+        if "long" not in path and "damaged" not in path:
+            monkeypatch.setenv("BLX_FLAC_GPU_MIN_SAMPLES", "0")
+        else:
+            monkeypatch.delenv("BLX_FLAC_GPU_MIN_SAMPLES", raising=False)
+        before = L.blx_flac_accelerated_count()
+        got = read_pcm_file(path)
+        assert L.blx_flac_accelerated_count() == before + (0 if "damaged" in path else 1), path
+        assert got[1:] == ref[1:] and np.array_equal(got[0], ref[0]), path
+    # and through the drop-in entry point: the golden force vector with the fixture decoded on the device
+    monkeypatch.setenv("BLX_FLAC_GPU_MIN_SAMPLES", "0")
+    s = bliss_b200.BlSong()
+    assert L.bl_analyze(files[0].encode(), ctypes.byref(s)) == 1
+    assert abs(s.force_vector.tempo - (-8.945454)) <= 1e-5 and abs(s.force_vector.attack - (-15.560563)) <= 1e-5
+    L.bl_free_song(ctypes.byref(s))
+
+
 def test_flac_frame_checksums_reject_damaged_frames(tmp_path):
     """A FLAC frame whose CRC-16 (or header CRC-8) does not match is dropped, not decoded as audio, and a sync code that
     happens to occur inside foreign bytes is not taken for a frame: the rest of the file decodes bit for bit."""

@@ -75,3 +75,42 @@ def test_threaded_decode_equals_sequential(tmp_path, monkeypatch):
             monkeypatch.setenv("BLX_DECODE_THREADS", threads)
             got = read_pcm_file(path)
             assert got[1:] == ref[1:] and np.array_equal(got[0], ref[0]), (path, threads)
+
+
+def test_device_decoder_logic_on_the_host(tmp_path, monkeypatch):
+    """The device FLAC decoder (csrc/flacdec.cu: one thread per frame, planar scratch, plain LPC loop, byte-wise CRC) is
+    compiled for the host as well; BLX_FLAC_EMULATE routes the reader's accelerator hook to that instance. Same samples as
+    the host decoder on the reference's fixtures and on encoder streams of every kind; a damaged file is refused by it and
+    decoded by the fall-back."""
+    import os
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    files = [os.path.join(golden, n) for n in ("song.flac", "song_s32.flac", "song_s32_mono.flac")]
+    rng = np.random.default_rng(99)
+    for bps, ch in ((16, 2), (24, 2), (12, 1)):
+        blocksize = 1152
+        pcm = _signal(rng, blocksize * 200, ch, bps)  # > 256 KB of frames: the chain scan is used
+
+        def plan(fi):
+            return dict(kind=KINDS[fi % 7], stereo=[None, 8, 9, 10][fi % 4] if ch == 2 else None, lpc_order=1 + (fi * 5) % 32,
+                        method=fi % 2, porder=[0, 1, 3, 5][fi % 4], escape_parts=(0,) if fi % 6 == 5 else ())
+
+        path = tmp_path / f"e{bps}_{ch}.flac"
+        path.write_bytes(encode(pcm, bps, 44100, blocksize, plan, seed=bps))
+        files.append(str(path))
+    blob = bytearray(open(files[0], "rb").read())
+    blob[len(blob) // 2] ^= 0x55
+    (tmp_path / "damaged.flac").write_bytes(bytes(blob))
+    files.append(str(tmp_path / "damaged.flac"))
+    import ctypes
+    import bliss_b200
+    count = ctypes.CDLL(bliss_b200.LIB_PATH).blx_flac_accelerated_count
+    for path in files:
+        monkeypatch.setenv("BLX_FLAC_GPU", "0")
+        ref = read_pcm_file(path)
+        monkeypatch.setenv("BLX_FLAC_GPU", "1")
+        monkeypatch.setenv("BLX_FLAC_GPU_MIN_SAMPLES", "0")
+        monkeypatch.setenv("BLX_FLAC_EMULATE", "1")
+        before = count()
+        got = read_pcm_file(path)
+        assert count() == before + (0 if "damaged" in path else 1), path  # the accelerator ran (and refused the damaged file)
+        assert got[1:] == ref[1:] and np.array_equal(got[0], ref[0]), path

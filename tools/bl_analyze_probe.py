@@ -57,6 +57,12 @@ def main():
                         struct.pack("<IHHIIHH", 16, 1, 2, 44100, 44100 * 4, 4, 16) + b"data" + struct.pack("<I", len(raw)) + raw)
             wav44.append(path.encode())
         fixture = os.path.join(ROOT, "tests", "golden", "song.flac").encode()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from flac_util import repeat_flac
+        long_flac = os.path.join(d, "long.flac")  # 177 s of 22 050 Hz stereo FLAC: the fixture's frames 16 times over
+        with open(long_flac, "wb") as f:
+            f.write(repeat_flac(fixture.decode(), 16))
+        long_flac = long_flac.encode()
         run(wavs, 16, 1)
         for rnd in range(3):
             rec = {"round": rnd}
@@ -66,6 +72,12 @@ def main():
                 rec[f"fixture_{th}"] = round(run([fixture] * 16, th, 4), 1)
             for th in (1, 8):
                 rec[f"wav44k_{th}"] = round(run(wav44, th, 2), 1)
+            for th in (1, 8):
+                rec[f"flac3min_gpu_{th}"] = round(run([long_flac] * 8, th, 2), 1)
+            os.environ["BLX_FLAC_GPU"] = "0"
+            for th in (1, 8):
+                rec[f"flac3min_cpu_{th}"] = round(run([long_flac] * 8, th, 2), 1)
+            del os.environ["BLX_FLAC_GPU"]
             print(json.dumps(rec), flush=True)
 
 
