@@ -140,8 +140,38 @@ FLAC_FN void fc_lpc_generic(int32_t *out, int n, int order, const int32_t *coef,
         }
     }
 }
+/* (the 32-bit form works on unsigned words, so a damaged file whose samples outgrow their declared width wraps around
+ * instead of running into signed overflow) */
+#define FC_LPC_BODY(ACC_T, ORD)                                                               \
+    for (int i = order; i < n; ++i) {                                                          \
+        ACC_T acc = 0;                                                                         \
+        const int32_t *h = out + i - (ORD);                                                    \
+        for (int k = 0; k < (ORD); ++k) acc += (ACC_T)rc[k] * (ACC_T)h[k];                     \
+        if (sizeof(ACC_T) == 4) out[i] = (int32_t)((uint32_t)((int32_t)acc >> shift) + (uint32_t)out[i]); \
+        else out[i] = (int32_t)(((int64_t)acc >> shift) + out[i]);                             \
+    }
+#define FC_LPC_SWITCH(ACC_T)                                                                  \
+    switch (order) {                                                                           \
+        case 1: FC_LPC_BODY(ACC_T, 1) break;   case 2: FC_LPC_BODY(ACC_T, 2) break;          \
+        case 3: FC_LPC_BODY(ACC_T, 3) break;   case 4: FC_LPC_BODY(ACC_T, 4) break;          \
+        case 5: FC_LPC_BODY(ACC_T, 5) break;   case 6: FC_LPC_BODY(ACC_T, 6) break;          \
+        case 7: FC_LPC_BODY(ACC_T, 7) break;   case 8: FC_LPC_BODY(ACC_T, 8) break;          \
+        case 9: FC_LPC_BODY(ACC_T, 9) break;   case 10: FC_LPC_BODY(ACC_T, 10) break;        \
+        case 11: FC_LPC_BODY(ACC_T, 11) break; case 12: FC_LPC_BODY(ACC_T, 12) break;        \
+        default: FC_LPC_BODY(ACC_T, order) break;                                             \
+    }
+
+
+/* The taps reversed once (the dot product then runs over contiguous samples), a loop with a constant trip count for the
+ * common orders (unrolled by the compiler: independent loads, a multiply-add tree), the plain loop for the rest. */
+FLAC_FN void fc_lpc_unrolled(int32_t *out, int n, int order, const int32_t *coef, int shift, int narrow) {
+    int32_t rc[32];
+    for (int k = 0; k < order; ++k) rc[k] = coef[order - 1 - k];
+    if (narrow) { FC_LPC_SWITCH(uint32_t) }
+    else { FC_LPC_SWITCH(int64_t) }
+}
 #ifndef FLAC_LPC
-#define FLAC_LPC fc_lpc_generic
+#define FLAC_LPC fc_lpc_unrolled
 #endif
 
 #ifndef BLX_RICE_FAST

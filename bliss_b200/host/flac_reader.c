@@ -60,32 +60,16 @@ static uint16_t crc16_of(const uint8_t *p, size_t n) {
     return c;
 }
 
+static void lpc_restore(int32_t *out, int n, int order, const int32_t *coef, int shift, int narrow);
+#define FLAC_LPC lpc_restore
+#define FLAC_CRC16 crc16_of
+#include "flac_core.h"
+
 /* LPC synthesis out[i] += (sum_j coef[j] out[i - 1 - j]) >> shift, i = order..n-1 (RFC 9639 section 9.2.6), the inner
  * loop of the decoder: the taps are reversed once so that the dot product runs over contiguous samples, the common
  * orders get a loop with a constant trip count (unrolled and vectorised by the compiler; an AVX2 clone is picked at
  * load time where the CPU has it), and 32-bit accumulators are used when bps + precision + log2(order) <= 32 bits
  * guarantees that nothing overflows them. */
-
-/* (the 32-bit form works on unsigned words, so a damaged file whose samples outgrow their declared width wraps around
- * instead of running into signed overflow) */
-#define BLX_LPC_BODY(ACC_T, ORD)                                                               \
-    for (int i = order; i < n; ++i) {                                                          \
-        ACC_T acc = 0;                                                                         \
-        const int32_t *h = out + i - (ORD);                                                    \
-        for (int k = 0; k < (ORD); ++k) acc += (ACC_T)rc[k] * (ACC_T)h[k];                     \
-        if (sizeof(ACC_T) == 4) out[i] = (int32_t)((uint32_t)((int32_t)acc >> shift) + (uint32_t)out[i]); \
-        else out[i] = (int32_t)(((int64_t)acc >> shift) + out[i]);                             \
-    }
-#define BLX_LPC_SWITCH(ACC_T)                                                                  \
-    switch (order) {                                                                           \
-        case 1: BLX_LPC_BODY(ACC_T, 1) break;   case 2: BLX_LPC_BODY(ACC_T, 2) break;          \
-        case 3: BLX_LPC_BODY(ACC_T, 3) break;   case 4: BLX_LPC_BODY(ACC_T, 4) break;          \
-        case 5: BLX_LPC_BODY(ACC_T, 5) break;   case 6: BLX_LPC_BODY(ACC_T, 6) break;          \
-        case 7: BLX_LPC_BODY(ACC_T, 7) break;   case 8: BLX_LPC_BODY(ACC_T, 8) break;          \
-        case 9: BLX_LPC_BODY(ACC_T, 9) break;   case 10: BLX_LPC_BODY(ACC_T, 10) break;        \
-        case 11: BLX_LPC_BODY(ACC_T, 11) break; case 12: BLX_LPC_BODY(ACC_T, 12) break;        \
-        default: BLX_LPC_BODY(ACC_T, order) break;                                             \
-    }
 
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(__SANITIZE_THREAD__) /* (TSan cannot run ifunc resolvers) */
 #define BLX_CLONES __attribute__((target_clones("avx2", "default"), optimize("O3")))
@@ -93,15 +77,8 @@ static uint16_t crc16_of(const uint8_t *p, size_t n) {
 #define BLX_CLONES
 #endif
 BLX_CLONES static void lpc_restore(int32_t *out, int n, int order, const int32_t *coef, int shift, int narrow) {
-    int32_t rc[32];
-    for (int k = 0; k < order; ++k) rc[k] = coef[order - 1 - k];
-    if (narrow) { BLX_LPC_SWITCH(uint32_t) }
-    else { BLX_LPC_SWITCH(int64_t) }
+    fc_lpc_unrolled(out, n, order, coef, shift, narrow); /* inlined into each clone */
 }
-
-#define FLAC_LPC lpc_restore
-#define FLAC_CRC16 crc16_of
-#include "flac_core.h"
 
 static void add_tag(blx_pcm_file *f, const char *kv, size_t len) {
     const char *eq = memchr(kv, '=', len);
