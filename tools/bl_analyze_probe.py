@@ -63,6 +63,18 @@ def main():
         with open(long_flac, "wb") as f:
             f.write(repeat_flac(fixture.decode(), 16))
         long_flac = long_flac.encode()
+        # CD audio in FLAC (44.1 kHz / 16 bit / stereo, 3 minutes): 6 s from the test encoder, its frames 30 times over
+        from flac_encode import encode
+        from synth import song_f32
+        x = song_f32(11, 6.0)
+        xs = np.round(np.stack([x * 0.9, np.roll(x, 23) * 0.6], axis=1) * 32767).astype(np.int64)
+        six = os.path.join(d, "six.flac")
+        with open(six, "wb") as f:
+            f.write(encode(xs, 16, 44100, 4096, lambda fi: dict(kind="lpc", stereo=10, lpc_order=8, porder=3), seed=3))
+        cd_flac = os.path.join(d, "cd.flac")
+        with open(cd_flac, "wb") as f:
+            f.write(repeat_flac(six, 30))
+        cd_flac = cd_flac.encode()
         run(wavs, 16, 1)
         for rnd in range(3):
             rec = {"round": rnd}
@@ -74,9 +86,13 @@ def main():
                 rec[f"wav44k_{th}"] = round(run(wav44, th, 2), 1)
             for th in (1, 8):
                 rec[f"flac3min_gpu_{th}"] = round(run([long_flac] * 8, th, 2), 1)
+            for th in (1, 8):
+                rec[f"cdflac_gpu_{th}"] = round(run([cd_flac] * 8, th, 2), 1)
             os.environ["BLX_FLAC_GPU"] = "0"
             for th in (1, 8):
                 rec[f"flac3min_cpu_{th}"] = round(run([long_flac] * 8, th, 2), 1)
+            for th in (1, 8):
+                rec[f"cdflac_cpu_{th}"] = round(run([cd_flac] * 8, th, 2), 1)
             del os.environ["BLX_FLAC_GPU"]
             print(json.dumps(rec), flush=True)
 
