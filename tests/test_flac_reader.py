@@ -114,3 +114,20 @@ def test_device_decoder_logic_on_the_host(tmp_path, monkeypatch):
         got = read_pcm_file(path)
         assert count() == before + (0 if "damaged" in path else 1), path  # the accelerator ran (and refused the damaged file)
         assert got[1:] == ref[1:] and np.array_equal(got[0], ref[0]), path
+
+
+def test_repeated_stream_helper(tmp_path, monkeypatch):
+    """flac_util.repeat_flac (renumbered, re-checksummed copies of a file's frames; what the GPU tests and probes use for
+    minutes of audio) decodes to the original PCM repeated, on the threaded host decoder and on the emulated device one."""
+    import os
+    from flac_util import repeat_flac
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "song.flac")
+    monkeypatch.setenv("BLX_FLAC_GPU", "0")
+    one = read_pcm_file(src)
+    (tmp_path / "r3.flac").write_bytes(repeat_flac(src, 3))
+    got = read_pcm_file(tmp_path / "r3.flac")
+    assert got[1] == 3 * one[1] and np.array_equal(got[0], np.tile(one[0], 3))
+    monkeypatch.setenv("BLX_FLAC_GPU", "1")
+    monkeypatch.setenv("BLX_FLAC_GPU_MIN_SAMPLES", "0")
+    monkeypatch.setenv("BLX_FLAC_EMULATE", "1")
+    assert np.array_equal(read_pcm_file(tmp_path / "r3.flac")[0], got[0])
