@@ -60,7 +60,7 @@ BLX_H_SYMBOLS = [
     "blx_analyze_batch_s16", "blx_analyze_batch_f32", "blx_analyze_batch_f32_exact", "blx_analyze_device", "blx_analyze_device_async", "blx_join",
     "blx_spectral_device",
     "blx_distance_matrix", "blx_cosine_matrix", "blx_distance_rows_device", "blx_distance_nearest_device", "blx_cosine_nearest_device",
-    "blx_mean_variance_s16", "blx_rectangular_filter", "blx_frontend_f32", "blx_resample_to_s16", "blx_resample_s16_to_s16", "blx_flac_decode_frames", "blx_flac_accelerated_count", "blx_envelope_energy_s16",
+    "blx_mean_variance_s16", "blx_rectangular_filter", "blx_frontend_f32", "blx_resample_to_s16", "blx_resample_s16_to_s16", "blx_flac_decode_frames", "blx_flac_decode_resample", "blx_flac_accelerated_count", "blx_envelope_energy_s16",
     "blx_frequency_spectrum_s16", "blx_histogram_s16", "blx_envelope_tail", "blx_envelope_energy_f32",
     "blx_profile_enable", "blx_profile_reset", "blx_profile_read", "blx_kernel_name", "blx_launch_count",
     "blx_measure_fp64_peak", "blx_multi_init", "blx_multi_shutdown", "blx_multi_device_count", "blx_multi_transport",

@@ -106,7 +106,7 @@ struct blx_engine {
     float prof_ms[BLX_K_COUNT] = {0};
     int prof_n[BLX_K_COUNT] = {0};
     long long launches = 0;
-    DevBuf scratch_a, scratch_b, scratch_near;
+    DevBuf scratch_a, scratch_b, scratch_c, scratch_near;
 };
 
 static const char *kKernelNames[BLX_K_COUNT] = {"pass1_kernel", "epilogue_kernel", "envelope_kernel", "tail_kernel",
@@ -279,6 +279,7 @@ extern "C" void blx_shutdown(blx_engine *e) {
     if (e->tail) cudaStreamDestroy(e->tail);
     e->scratch_a.release();
     e->scratch_b.release();
+    e->scratch_c.release();
     e->scratch_near.release();
     for (auto &r : e->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
@@ -894,12 +895,40 @@ extern "C" int blx_resample_s16_to_s16(blx_engine *e, const int16_t *samples, in
 // FLAC frames on the device (flacdec.cu). `hdr` is the host reader's chain of frames (flac_hdr[n_frames], 40 bytes each,
 // host/flac_core.h), `first` the first sample of every frame; out receives samples * channels interleaved int16 (out16)
 // or int32 values. BLX_ERR_ARG with "frame" in the message = a frame did not check out: decode on the host instead.
-extern "C" int blx_flac_decode_frames(blx_engine *e, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first,
-                                      int n_frames, int channels, int out16, uint64_t samples, void *out) {
+// in_rate > 0: a 16-bit mono / stereo stream that is not in the analysers' format - the decoded PCM stays on the device
+// and goes straight through the decode-stage resampler; `out` then receives the int16 / 22 050 Hz / stereo result
+// (*n_out_frames frames, capacity out_capacity_frames; out == NULL only sizes it).
+static int flac_decode_impl(blx_engine *e, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, int n_frames,
+                            int channels, int out16, uint64_t samples, void *out, int in_rate, int64_t out_capacity_frames,
+                            int64_t *n_out_frames) {
     int rc = check_engine(e);
     if (rc) return rc;
-    if (!file || !hdr || !first || !out || n_frames <= 0 || channels < 1 || channels > 8 || samples == 0 || samples > ((uint64_t)1 << 32))
+    if (!file || !hdr || !first || n_frames <= 0 || channels < 1 || channels > 8 || samples == 0 || samples > ((uint64_t)1 << 32))
         return fail(BLX_ERR_ARG, "bad FLAC decode arguments");
+    ResampleParams rp;
+    memset(&rp, 0, sizeof(rp));
+    std::vector<float> bank;
+    if (in_rate > 0) {
+        if (!out16 || channels > 2 || !n_out_frames) return fail(BLX_ERR_ARG, "the fused resampler takes 16-bit mono / stereo streams");
+        rp.kind = BLX_RS_KIND_S16; rp.bits = 16; rp.channels = channels; rp.n_in = (long long)samples;
+        if (in_rate == BLX_RS_OUT_RATE) {
+            rp.n_out = (long long)samples;
+        } else {
+            blx_rs_plan plan;
+            if (blx_rs_plan_make(in_rate, BLX_RS_OUT_RATE, &plan))
+                return fail(BLX_ERR_ARG, "sample rate %d Hz needs more than %d filter phases", in_rate, BLX_RS_MAX_PHASES);
+            rp.L = plan.L; rp.P = plan.P; rp.q = plan.q; rp.center = plan.center;
+            rp.mono_gain_last = BLX_RS_MONO_GAIN_LAST(in_rate) ? 1 : 0;
+            rp.n_out = blx_rs_out_frames(&plan, (long long)samples, nullptr);
+            bank.resize((size_t)plan.P * plan.L);
+            blx_rs_build_f32(&plan, bank.data());
+        }
+        *n_out_frames = rp.n_out;
+        if (!out) return BLX_OK; // size query
+        if (out_capacity_frames < rp.n_out || rp.n_out <= 0) return fail(BLX_ERR_ARG, "output buffer too small or empty stream");
+    } else if (!out) {
+        return fail(BLX_ERR_ARG, "null output");
+    }
     const size_t hdr_bytes = (size_t)n_frames * 40, first_bytes = (size_t)n_frames * 8;
     const size_t o_hdr = (n_bytes + 255) & ~(size_t)255, o_first = o_hdr + ((hdr_bytes + 255) & ~(size_t)255);
     const size_t o_fail = o_first + ((first_bytes + 255) & ~(size_t)255);
@@ -923,10 +952,39 @@ extern "C" int blx_flac_decode_frames(blx_engine *e, const uint8_t *file, size_t
     CK(launch_flac_decode(p, st));
     int failed = 0;
     CK(cudaMemcpyAsync(&failed, p.fail, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out, p.out, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (in_rate > 0) {
+        // decoded PCM (device) -> resampler -> host; the decoded stream itself never leaves the device
+        const size_t rs_out_bytes = (size_t)rp.n_out * 2 * 2, bank_bytes = bank.size() * 4;
+        CK(e->scratch_c.reserve(((rs_out_bytes + 255) & ~(size_t)255) + bank_bytes + 256));
+        unsigned char *c = static_cast<unsigned char *>(e->scratch_c.p);
+        unsigned char *d_bank = c + ((rs_out_bytes + 255) & ~(size_t)255);
+        if (bank_bytes) CK(cudaMemcpyAsync(d_bank, bank.data(), bank_bytes, cudaMemcpyHostToDevice, st));
+        rp.in = nullptr;
+        rp.in16 = static_cast<const short *>(p.out);
+        rp.out = reinterpret_cast<short *>(c);
+        rp.bank_f32 = reinterpret_cast<const float *>(d_bank);
+        rp.bank_s16 = reinterpret_cast<const short *>(d_bank);
+        e->launches++;
+        CK(launch_resample(rp, st));
+        CK(cudaMemcpyAsync(out, c, rs_out_bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        CK(cudaMemcpyAsync(out, p.out, out_bytes, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     if (failed) return fail(BLX_ERR_ARG, "a FLAC frame did not decode on the device (damaged stream or a false frame boundary)");
     return BLX_OK;
+}
+
+extern "C" int blx_flac_decode_frames(blx_engine *e, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first,
+                                      int n_frames, int channels, int out16, uint64_t samples, void *out) {
+    return flac_decode_impl(e, file, n_bytes, hdr, first, n_frames, channels, out16, samples, out, 0, 0, nullptr);
+}
+
+extern "C" int blx_flac_decode_resample(blx_engine *e, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first,
+                                        int n_frames, int channels, uint64_t samples, int in_rate, int16_t *out,
+                                        int64_t out_capacity_frames, int64_t *n_out_frames) {
+    if (in_rate <= 0) return fail(BLX_ERR_ARG, "bad sample rate");
+    return flac_decode_impl(e, file, n_bytes, hdr, first, n_frames, channels, 1, samples, out, in_rate, out_capacity_frames, n_out_frames);
 }
 
 // 44.1 kHz (or any-rate) mono / stereo float32 host buffers -> the decode-stage resampler on the device -> the native

@@ -29,24 +29,42 @@ int blx_flac_decode_frames_emulated(const unsigned char *file, size_t n_bytes, c
 static int g_flac_accel_ok = 0; /* streams the accelerator decoded (diagnostic; tests assert that it ran) */
 int blx_flac_accelerated_count(void) { return __atomic_load_n(&g_flac_accel_ok, __ATOMIC_RELAXED); }
 
-static int flac_on_device_impl(const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames, int channels,
-                               int out16, uint64_t samples, void *out);
-static int flac_on_device(const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames, int channels,
-                          int out16, uint64_t samples, void *out) {
-    const int rc = flac_on_device_impl(file, n_bytes, hdr, first, n_frames, channels, out16, samples, out);
+static __thread int t_want_fused = 0; /* bl_audio_decode is the caller: a stream that needs the resampler may get it on the device */
+static int flac_on_device_impl(blx_pcm_file *f, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames,
+                               int channels, int out16, uint64_t samples, void *out);
+static int flac_on_device(blx_pcm_file *f, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames,
+                          int channels, int out16, uint64_t samples, void *out) {
+    const int rc = flac_on_device_impl(f, file, n_bytes, hdr, first, n_frames, channels, out16, samples, out);
     if (rc == 0) __atomic_add_fetch(&g_flac_accel_ok, 1, __ATOMIC_RELAXED);
     return rc;
 }
 
-static int flac_on_device_impl(const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames, int channels,
-                          int out16, uint64_t samples, void *out) {
+static int flac_on_device_impl(blx_pcm_file *f, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, size_t n_frames,
+                               int channels, int out16, uint64_t samples, void *out) {
     if (n_frames > 0x7fffffff) return -1;
     if (getenv("BLX_FLAC_EMULATE")) /* tests without a GPU: the host instance of the device code */
         return blx_flac_decode_frames_emulated(file, n_bytes, hdr, (const unsigned long long *)first, (int)n_frames, channels, out16,
                                                samples, out);
     blx_engine *e = bl_engine_acquire();
     if (!e) return -1;
-    const int rc = blx_flac_decode_frames(e, file, n_bytes, hdr, first, (int)n_frames, channels, out16, samples, out);
+    int rc;
+    if (t_want_fused && out16 && channels <= 2 && f->sample_rate > 0 && f->sample_rate != BLX_RS_OUT_RATE) {
+        /* CD audio and the like: decode and resample in one go, only the 22 050 Hz result comes back */
+        int64_t n_out = 0;
+        int16_t *pcm = NULL;
+        rc = blx_flac_decode_resample(e, file, n_bytes, hdr, first, (int)n_frames, channels, samples, f->sample_rate, NULL, 0, &n_out);
+        if (rc == BLX_OK && n_out > 0 && n_out < ((int64_t)1 << 30)) pcm = (int16_t *)malloc((size_t)n_out * 2 * sizeof(int16_t));
+        else if (rc == BLX_OK) rc = BLX_ERR_ARG;
+        if (pcm) {
+            rc = blx_flac_decode_resample(e, file, n_bytes, hdr, first, (int)n_frames, channels, samples, f->sample_rate, pcm, n_out, &n_out);
+            if (rc == BLX_OK) { f->resampled16 = pcm; f->resampled_frames = (size_t)n_out; }
+            else free(pcm);
+        } else if (rc == BLX_OK) {
+            rc = BLX_ERR_NOMEM;
+        }
+    } else {
+        rc = blx_flac_decode_frames(e, file, n_bytes, hdr, first, (int)n_frames, channels, out16, samples, out);
+    }
     bl_engine_release();
     return rc == BLX_OK ? 0 : -1;
 }
@@ -55,7 +73,10 @@ __attribute__((constructor)) static void install_flac_accel(void) { blx_flac_acc
 int bl_audio_decode(char const *const filename, struct bl_song *const song) {
     blx_pcm_file f;
     bl_initialize_song(song);
-    if (blx_pcm_file_read(filename, &f) != 0) {
+    t_want_fused = 1;
+    const int read_rc = blx_pcm_file_read(filename, &f);
+    t_want_fused = 0;
+    if (read_rc != 0) {
         fprintf(stderr, "Couldn't open file: %s (not a readable FLAC or WAV file)\n", filename);
         return BL_UNEXPECTED;
     }
@@ -84,7 +105,14 @@ int bl_audio_decode(char const *const filename, struct bl_song *const song) {
      * int32, float PCM as float, 8-bit PCM as unsigned bytes */
     const int is_u8 = f.container == 1 && !f.is_float && f.bits_per_sample == 8;
     const int is_s16 = !f.is_float && !is_u8 && f.bits_per_sample <= 16;
-    if (f.sample_rate == BLX_RS_OUT_RATE && is_s16 && (f.channels == 1 || f.channels == 2)) {
+    if (f.resampled16) {
+        /* a long FLAC stream that the device decoded AND resampled (flac_on_device) */
+        song->sample_array = (int8_t *)f.resampled16;
+        song->nSamples = (int)(2 * f.resampled_frames);
+        song->resampled = 1;
+        f.resampled16 = NULL;
+        rc = BL_OK;
+    } else if (f.sample_rate == BLX_RS_OUT_RATE && is_s16 && (f.channels == 1 || f.channels == 2)) {
         /* native format: copied through untouched (a mono file keeps its mono sample count while
          * channels reads 2, exactly as reference src/decode.c:187-193 leaves it) */
         const size_t n = f.n_frames * (size_t)f.channels;

@@ -265,10 +265,11 @@ static int decode_flac_parallel(const uint8_t *d, size_t n, size_t pos, uint64_t
             const unsigned long long min_samples = mn ? strtoull(mn, NULL, 10) : 4000000ull; /* ~45 s of CD audio */
             if (blx_flac_accel && !(sw && sw[0] == '0') && (unsigned long long)samples * (unsigned)f->channels >= min_samples &&
                 sizeof(size_t) == sizeof(uint64_t) &&
-                blx_flac_accel(d, n, hdr, (const uint64_t *)first, nf, f->channels, job.out16, (uint64_t)samples, job.pcm) == 0) {
+                blx_flac_accel(f, d, n, hdr, (const uint64_t *)first, nf, f->channels, job.out16, (uint64_t)samples, job.pcm) == 0) {
                 size_t nframes = samples;
                 if (total && nframes > total) nframes = (size_t)total;
-                if (job.out16) f->samples16 = (int16_t *)job.pcm;
+                if (f->resampled16) free(job.pcm); /* the accelerator resampled on the device as well: nothing decoded comes back */
+                else if (job.out16) f->samples16 = (int16_t *)job.pcm;
                 else f->samples = (int32_t *)job.pcm;
                 f->n_frames = nframes;
                 rc = 0;
@@ -536,6 +537,7 @@ int blx_pcm_file_read(const char *filename, blx_pcm_file *f) {
 void blx_pcm_file_free(blx_pcm_file *f) {
     free(f->samples);
     free(f->samples16);
+    free(f->resampled16);
     free(f->artist); free(f->title); free(f->album); free(f->tracknumber); free(f->genre);
     memset(f, 0, sizeof(*f));
 }

@@ -215,6 +215,13 @@ int blx_resample_s16_to_s16(blx_engine *e, const int16_t *samples, int channels,
 int blx_flac_decode_frames(blx_engine *e, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, int n_frames,
                            int channels, int out16, uint64_t samples, void *out);
 
+/* The same for a 16-bit mono / stereo stream that still needs the decode-stage resampler (CD audio): the decoded PCM stays on
+ * the device and goes straight through blx_resample.h; `out` receives int16 / 22 050 Hz / stereo, *n_out_frames frames.
+ * out == NULL only returns the number of output frames. */
+int blx_flac_decode_resample(blx_engine *e, const uint8_t *file, size_t n_bytes, const void *hdr, const uint64_t *first, int n_frames,
+                             int channels, uint64_t samples, int in_rate, int16_t *out, int64_t out_capacity_frames,
+                             int64_t *n_out_frames);
+
 /* Diagnostic: how many FLAC streams bl_audio_decode has decoded through the device decoder so far in this process. */
 int blx_flac_accelerated_count(void);
 

@@ -127,7 +127,7 @@ def test_files_at_other_rates_and_formats_go_through_the_resampler(tmp_path, ora
 
 
 @pytest.mark.gpu
-def test_cd_audio_flac_goes_through_the_resampler(tmp_path, oracle):
+def test_cd_audio_flac_goes_through_the_resampler(tmp_path, oracle, monkeypatch):
     """The everyday input: 44.1 kHz / 16 bit / stereo FLAC (here from the test encoder; large enough for the threaded
     decoder). Decoded straight to int16, resampled on the GPU as int16, analysed: PCM equal to the oracle resampler's, force
     vector equal to the reference analysers' on that PCM. A 12-bit mono FLAC at 32 kHz takes the int32 route."""
@@ -136,11 +136,16 @@ def test_cd_audio_flac_goes_through_the_resampler(tmp_path, oracle):
     xs = np.round(np.stack([x * 0.9, np.roll(x, 23) * 0.6], axis=1) * 32767).astype(np.int64)
     plan = lambda fi: dict(kind=["lpc", "fixed2", "fixed4"][fi % 3], stereo=[None, 8, 9, 10][fi % 4], lpc_order=1 + (fi * 3) % 12, porder=3)
     (tmp_path / "cd.flac").write_bytes(encode(xs, 16, 44100, 4096, plan, seed=3))
-    L, s, rc = decode(tmp_path / "cd.flac")
-    assert rc == 0 and s.resampled == 1 and s.channels == 2 and s.sample_rate == 22050 and s.duration == 6
     want = oracle.resample_to_s16(xs.astype(np.int32).reshape(-1), oracle.RS_S16, 16, 2, 44100)
-    assert np.array_equal(pcm_of(s), want)
-    L.bl_free_song(ctypes.byref(s))
+    for forced in (False, True):  # host decode + resampler call; then decode AND resampling fused on the device
+        if forced:
+            monkeypatch.setenv("BLX_FLAC_GPU_MIN_SAMPLES", "0")
+        before = bliss_b200.load().blx_flac_accelerated_count()
+        L, s, rc = decode(tmp_path / "cd.flac")
+        assert L.blx_flac_accelerated_count() == before + (1 if forced else 0)
+        assert rc == 0 and s.resampled == 1 and s.channels == 2 and s.sample_rate == 22050 and s.duration == 6
+        assert s.nSamples == len(want) and np.array_equal(pcm_of(s), want), forced
+        L.bl_free_song(ctypes.byref(s))
     s2 = bliss_b200.BlSong()
     assert L.bl_analyze(str(tmp_path / "cd.flac").encode(), ctypes.byref(s2)) in (0, 1)
     ref = oracle.analyze(want, 6)

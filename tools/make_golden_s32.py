@@ -18,7 +18,8 @@ rd = ctypes.CDLL(so)
 class PcmFile(ctypes.Structure):
     _fields_ = [("samples", ctypes.POINTER(ctypes.c_int32)), ("samples16", ctypes.POINTER(ctypes.c_int16)), ("n_frames", ctypes.c_size_t), ("channels", ctypes.c_int),
                 ("sample_rate", ctypes.c_int), ("bits_per_sample", ctypes.c_int), ("is_float", ctypes.c_int), ("container", ctypes.c_int),
-                ("file_bytes", ctypes.c_uint64), ("md5", ctypes.c_uint8 * 16)] + [(k, ctypes.c_char_p) for k in ("artist", "title", "album", "tracknumber", "genre")]
+                ("file_bytes", ctypes.c_uint64), ("md5", ctypes.c_uint8 * 16)] + [(k, ctypes.c_char_p) for k in ("artist", "title", "album", "tracknumber", "genre")] + [
+                    ("resampled16", ctypes.POINTER(ctypes.c_int16)), ("resampled_frames", ctypes.c_size_t)]
 rd.blx_pcm_file_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(PcmFile)]
 def read(path):
     f = PcmFile()
