@@ -514,6 +514,25 @@ def bl_analyze_leg(torch, buf, stride, n_in, n_files=8):
                         struct.pack("<IHHIIHH", 16, 1, 2, 44100, 44100 * 4, 4, 16) + b"data" + struct.pack("<I", len(raw)) + raw)
             cd_wavs.append(path.encode())
         fixture = os.path.join(ROOT, "tests", "golden", "song.flac").encode()
+        # three minutes of FLAC: the fixture's frames 16 times over (22 050 Hz: device decode, native format) and six
+        # seconds of CD audio from the test encoder 30 times over (44.1 kHz: device decode + resampler fused)
+        flacs = {}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from flac_encode import encode
+            from flac_util import repeat_flac
+            with open(os.path.join(d, "long.flac"), "wb") as f:
+                f.write(repeat_flac(fixture.decode(), 16))
+            flacs["flac_3min_22k"] = os.path.join(d, "long.flac").encode()
+            six = buf[:6 * 44100].cpu().numpy().astype(np.float64)
+            xs = np.round(np.stack([six * 0.9, np.roll(six, 23) * 0.6], axis=1) * 32767).astype(np.int64)
+            with open(os.path.join(d, "six.flac"), "wb") as f:
+                f.write(encode(xs, 16, 44100, 4096, lambda fi: dict(kind="lpc", stereo=10, lpc_order=8, porder=3), seed=3))
+            with open(os.path.join(d, "cd.flac"), "wb") as f:
+                f.write(repeat_flac(os.path.join(d, "six.flac"), 30))
+            flacs["flac_3min_cd_44k"] = os.path.join(d, "cd.flac").encode()
+        except Exception as ex:  # the leg is informative: never fail the bench over a helper
+            flacs = {"error": repr(ex)}
 
         def run(files, threads, reps):
             recs, lock = {}, threading.Lock()
@@ -557,11 +576,23 @@ def bl_analyze_leg(torch, buf, stride, n_in, n_files=8):
         run(cd_wavs[:1], 1, 1)
         cd1, _ = median_of(cd_wavs, 1, 1)
         cd4, _ = median_of(cd_wavs, 4, 2)
+        flac_rates = {}
+        for name, path in flacs.items():
+            if name == "error":
+                flac_rates[name] = path
+                continue
+            run([path], 1, 1)
+            flac_rates[name + "_songs_per_s_1_thread"], _ = median_of([path] * 4, 1, 1)
+            flac_rates[name + "_songs_per_s_4_threads"], _ = median_of([path] * 4, 4, 2)
+            os.environ["BLX_FLAC_GPU"] = "0"  # the same with the four host decode threads instead of the device decoder
+            flac_rates[name + "_host_decode_songs_per_s_1_thread"], _ = median_of([path] * 4, 1, 1)
+            del os.environ["BLX_FLAC_GPU"]
         out = {"api": "bl_analyze (include/bliss.h), one file per call: host read + decode, GPU analysis",
                "wav_3min_songs_per_s_1_thread": one, "wav_3min_songs_per_s_8_threads": many,
                "fixture_11s_songs_per_s_1_thread": fx1, "fixture_11s_songs_per_s_8_threads": fx8,
                "cd_wav_44k_3min_songs_per_s_1_thread": cd1, "cd_wav_44k_3min_songs_per_s_4_threads": cd4,
                "results_identical_across_threads": bool(same), "files": n_files, "statistic": "median of 3 trials"}
+        out.update(flac_rates)
     return out
 
 
