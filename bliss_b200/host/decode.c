@@ -45,6 +45,9 @@ static int flac_on_device_impl(blx_pcm_file *f, const uint8_t *file, size_t n_by
     if (getenv("BLX_FLAC_EMULATE")) /* tests without a GPU: the host instance of the device code */
         return blx_flac_decode_frames_emulated(file, n_bytes, hdr, (const unsigned long long *)first, (int)n_frames, channels, out16,
                                                samples, out);
+    static int have_gpu = -1; /* asked once: without a device the host threads decode (nothing is printed) */
+    if (have_gpu < 0) have_gpu = blx_device_count() > 0;
+    if (!have_gpu) return -1;
     blx_engine *e = bl_engine_acquire();
     if (!e) return -1;
     int rc;

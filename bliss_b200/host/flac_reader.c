@@ -262,7 +262,7 @@ static int decode_flac_parallel(const uint8_t *d, size_t n, size_t pos, uint64_t
         /* long streams: the device decoder, if the library provides one (BLX_FLAC_GPU=0 turns it off) */
         {
             const char *sw = getenv("BLX_FLAC_GPU"), *mn = getenv("BLX_FLAC_GPU_MIN_SAMPLES");
-            const unsigned long long min_samples = mn ? strtoull(mn, NULL, 10) : 4000000ull; /* ~45 s of CD audio */
+            const unsigned long long min_samples = mn ? strtoull(mn, NULL, 10) : 1000000ull; /* measured crossover ~0.7 M (tools/flac_gpu_probe.py) */
             if (blx_flac_accel && !(sw && sw[0] == '0') && (unsigned long long)samples * (unsigned)f->channels >= min_samples &&
                 sizeof(size_t) == sizeof(uint64_t) &&
                 blx_flac_accel(f, d, n, hdr, (const uint64_t *)first, nf, f->channels, job.out16, (uint64_t)samples, job.pcm) == 0) {
